@@ -1,0 +1,171 @@
+"""Host-side engine: device memory and streams through torch, compute through the C ABI.
+
+PyTorch is plumbing here (allocation, H2D/D2H copies, streams, torch.distributed); every
+operation of the dense hot path is a hand-written sm_100a kernel behind include/b200dense.h.
+There is no CPU path: constructing a DenseEngine without CUDA raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import B200DenseError, Cams, PmParams, Rng
+
+
+def kinv32(K_scaled: np.ndarray) -> np.ndarray:
+    """fp32 inverse of the working-resolution intrinsics, the way the reference gets it
+    (`torch.inverse(K)` on an fp32 tensor, mvs_patchmatch.py:237-238, dense_stereo.py:232-233),
+    evaluated on the host so both sides of every parity check see the same bits."""
+    return torch.inverse(torch.from_numpy(np.asarray(K_scaled, dtype=np.float64).astype(np.float32))).numpy()
+
+
+def make_cams(K_scaled, Kinv32, R_ref, t_ref, R_src: Sequence, t_src: Sequence) -> Cams:
+    """Pack the fp32 camera block (f64 -> f32 casts as in mvs_patchmatch.py:237-257)."""
+    if not 1 <= len(R_src) <= _cabi.MAX_SRC:
+        raise ValueError(f"need 1..{_cabi.MAX_SRC} source views, got {len(R_src)}")
+    c = Cams()
+    f = np.float32
+    c.K[:] = np.asarray(K_scaled, dtype=np.float64).astype(f).ravel().tolist()
+    c.Kinv[:] = np.asarray(Kinv32, dtype=f).ravel().tolist()
+    c.R_ref[:] = np.asarray(R_ref, dtype=np.float64).astype(f).ravel().tolist()
+    c.t_ref[:] = np.asarray(t_ref, dtype=np.float64).astype(f).ravel().tolist()
+    c.n_src = len(R_src)
+    for s, (R, t) in enumerate(zip(R_src, t_src)):
+        c.R_src[s][:] = np.asarray(R, dtype=np.float64).astype(f).ravel().tolist()
+        c.t_src[s][:] = np.asarray(t, dtype=np.float64).astype(f).ravel().tolist()
+    return c
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "device tensors must be contiguous CUDA tensors"
+    return t.data_ptr()
+
+
+def _ptr_array(ts: Sequence[torch.Tensor]):
+    arr = (C.c_void_p * len(ts))(*[_ptr(t) for t in ts])
+    return arr
+
+
+class DenseEngine:
+    """One engine per GPU (one process per GPU).  Owns cached scratch buffers."""
+
+    def __init__(self, device: str | torch.device | int = 'cuda:0'):
+        if not torch.cuda.is_available():
+            raise B200DenseError("CUDA is not available: the dense path has no CPU fallback")
+        self.lib = _cabi.load()
+        self.device = torch.device(device if not isinstance(device, int) else f'cuda:{device}')
+        if self.device.type != 'cuda':
+            raise B200DenseError(f"DenseEngine needs a CUDA device, got {self.device}")
+        torch.cuda.set_device(self.device)
+        self._scratch: Dict[Tuple[str, int, int], torch.Tensor] = {}
+        self.launches = 0                     # kernels of ours enqueued (bench's gpu_launches claim)
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def scratch(self, kind: str, H: int, W: int) -> torch.Tensor:
+        key = (kind, H, W)
+        buf = self._scratch.get(key)
+        if buf is None:
+            nbytes = {'pm': self.lib.b200d_pm_scratch_bytes, 'sweep': self.lib.b200d_sweep_scratch_bytes,
+                      'fuse': self.lib.b200d_fuse_scratch_bytes}[kind](H, W)
+            buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
+            self._scratch[key] = buf
+        return buf
+
+    def to_device(self, a: np.ndarray, dtype=torch.float32) -> torch.Tensor:
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        return t.to(self.device, dtype=dtype, non_blocking=True).contiguous()
+
+    # ------------------------------------------------------------------ entry points
+    def ref_stats(self, ref: torch.Tensor, patch: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        H, W = ref.shape
+        mean1 = torch.empty_like(ref)
+        var1 = torch.empty_like(ref)
+        _cabi.check(self.lib.b200d_ref_stats(_ptr(ref), H, W, patch, _ptr(mean1), _ptr(var1), self._stream()))
+        self.launches += 1
+        return mean1, var1
+
+    def pm_cost(self, ref: torch.Tensor, srcs: Sequence[torch.Tensor], cams: Cams, depth: torch.Tensor, patch: int,
+                mode: int = 0, arith: int = _cabi.PARITY, stats=None) -> torch.Tensor:
+        H, W = ref.shape
+        mean1, var1 = stats if stats is not None else self.ref_stats(ref, patch)
+        out = torch.empty_like(ref)
+        _cabi.check(self.lib.b200d_pm_cost(_ptr(ref), _ptr(mean1), _ptr(var1), _ptr_array(srcs), C.byref(cams),
+                                           _ptr(depth), H, W, patch, mode, arith, _ptr(out), self._stream()))
+        self.launches += 1
+        return out
+
+    def pm_view(self, ref: torch.Tensor, srcs: Sequence[torch.Tensor], cams: Cams, patch: int, iters: int,
+                samples: int, depth_min: float, depth_max: float, *, seed: int = 0, view_id: int = 0,
+                init_depth: Optional[torch.Tensor] = None, init_normal: Optional[torch.Tensor] = None,
+                rand_u: Optional[torch.Tensor] = None, rand_n: Optional[torch.Tensor] = None,
+                arith: int = _cabi.PARITY, dump_costs: bool = False, want_best: bool = False, out=None):
+        """Full PatchMatch of one reference view (mvs_patchmatch.py:225-321); returns device tensors
+        dict(depth, normal, confidence[, best_cost, costs])."""
+        H, W = ref.shape
+        prm = PmParams(patch=patch, iters=iters, samples=samples, arith=arith,
+                       depth_min=float(depth_min), depth_max=float(depth_max))
+        rng = Rng(seed=seed, view_id=view_id, d_init_depth=_ptr(init_depth), d_init_normal=_ptr(init_normal),
+                  d_rand_u=_ptr(rand_u), d_rand_n=_ptr(rand_n))
+        if out is None:
+            out = dict(depth=torch.empty((H, W), dtype=torch.float32, device=self.device),
+                       normal=torch.empty((H, W, 3), dtype=torch.float32, device=self.device),
+                       confidence=torch.empty((H, W), dtype=torch.float32, device=self.device))
+        best = torch.empty((H, W), dtype=torch.float32, device=self.device) if want_best else None
+        costs = (torch.empty((iters * (2 + samples), H, W), dtype=torch.float32, device=self.device)
+                 if dump_costs else None)
+        _cabi.check(self.lib.b200d_pm_view(_ptr(ref), _ptr_array(srcs), C.byref(cams), H, W, C.byref(prm), C.byref(rng),
+                                           _ptr(self.scratch('pm', H, W)), _ptr(out['depth']), _ptr(out['normal']),
+                                           _ptr(out['confidence']), _ptr(best), _ptr(costs), self._stream()))
+        self.launches += 2 + iters * (2 + samples) + 1          # stats, init, evaluations, confidence
+        if want_best:
+            out['best_cost'] = best
+        if dump_costs:
+            out['costs'] = costs
+        return out
+
+    def plane_sweep(self, ref: torch.Tensor, nbrs: Sequence[torch.Tensor], cams: Cams, depths: torch.Tensor,
+                    patch: int, thresh: float, arith: int = _cabi.PARITY, dump_ncc: bool = False):
+        """Plane sweep of one reference view (dense_stereo.py:222-316); device tensors."""
+        H, W = ref.shape
+        D = depths.numel()
+        depth_map = torch.empty((H, W), dtype=torch.float32, device=self.device)
+        conf = torch.empty((H, W), dtype=torch.float32, device=self.device)
+        idx = torch.empty((H, W), dtype=torch.int32, device=self.device)
+        ncc = torch.empty((D, len(nbrs), H, W), dtype=torch.float32, device=self.device) if dump_ncc else None
+        _cabi.check(self.lib.b200d_plane_sweep(_ptr(ref), _ptr_array(nbrs), C.byref(cams), _ptr(depths), D, H, W, patch,
+                                               float(thresh), arith, _ptr(depth_map), _ptr(conf), _ptr(idx), _ptr(ncc),
+                                               _ptr(self.scratch('sweep', H, W)), self._stream()))
+        self.launches += 2
+        return dict(depth_map=depth_map, confidence=conf, best_idx=idx, ncc=ncc)
+
+    def mask_backproject(self, depth: torch.Tensor, conf: torch.Tensor, bgr: torch.Tensor, Kinv64: np.ndarray,
+                         R: np.ndarray, t: np.ndarray, min_conf: float, mode: int,
+                         points: Optional[torch.Tensor] = None, colors: Optional[torch.Tensor] = None):
+        """Mask + ordered compaction + back-projection (mvs_patchmatch.py:545-565 / dense_stereo.py:414-437).
+        Returns (points (M,3) f64, colors (M,3) u8) device tensors; synchronises to read M."""
+        H, W = depth.shape
+        if points is None:
+            points = torch.empty((H * W, 3), dtype=torch.float64, device=self.device)
+        if colors is None:
+            colors = torch.empty((H * W, 3), dtype=torch.uint8, device=self.device)
+        count = torch.zeros(1, dtype=torch.int64, device=self.device)
+        Ki = np.ascontiguousarray(Kinv64, dtype=np.float64)
+        Rm = np.ascontiguousarray(R, dtype=np.float64)
+        tv = np.ascontiguousarray(t, dtype=np.float64).ravel()
+        dp = C.POINTER(C.c_double)
+        _cabi.check(self.lib.b200d_mask_backproject(_ptr(depth), _ptr(conf), _ptr(bgr), H, W, Ki.ctypes.data_as(dp),
+                                                    Rm.ctypes.data_as(dp), tv.ctypes.data_as(dp), float(min_conf), mode,
+                                                    _ptr(points), _ptr(colors), _ptr(count),
+                                                    _ptr(self.scratch('fuse', H, W)), self._stream()))
+        self.launches += 3
+        m = int(count.item())
+        return points[:m], colors[:m]

@@ -1,0 +1,149 @@
+/*
+ * b200dense.h -- C ABI of the B200-native dense-reconstruction hot path.
+ *
+ * Drop-in boundary for Stage 4 of dackey-wav/3d-reconstruction-tool.  The reference has no
+ * FFI of its own: its boundary is the Python class API, and every device
+ * operation is a PyTorch eager call.  Each entry point below replaces one reference method
+ * (cited as /root/reference-relative file:line) and is what a ctypes binding inside those
+ * methods would call (INTEGRATION.md shows the stubs).
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; all image-like buffers are row-major, contiguous.
+ *   - pointers named d_* are DEVICE pointers (sm_100a), everything else is host memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls only
+ *     enqueue work; they never synchronise unless stated.  Thread-safe per stream.
+ *   - return value: 0 on success, negative b200d_status on error; b200d_last_error() gives the
+ *     message for the calling thread.  No exceptions cross the boundary, nothing is printed.
+ *   - caller owns every buffer; the library allocates nothing unless stated.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns
+ *     B200D_ERR_CUDA.
+ *
+ * Arithmetic modes
+ *   B200D_PARITY  IEEE-RN fp32 in the exact operation order of the reference's CPU path
+ *                 (SURVEY.md §7.4): bit-identical to oracle/dense_oracle.c.
+ *   B200D_FAST    same algorithm, re-associated for speed (composed reprojection, sliding
+ *                 window sums); NCC agrees to ~1e-5, not bit-exact.
+ */
+#ifndef B200DENSE_H
+#define B200DENSE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B200D_API __attribute__((visibility("default")))
+#else
+#define B200D_API
+#endif
+
+#define B200D_MAX_SRC 8          /* source / neighbour views per reference view */
+#define B200D_ABI_VERSION 1
+
+typedef enum {
+    B200D_OK = 0,
+    B200D_ERR_ARG = -1,          /* bad pointer / size / unsupported patch size */
+    B200D_ERR_CUDA = -2,         /* CUDA runtime error (message in b200d_last_error) */
+    B200D_ERR_UNSUPPORTED = -3
+} b200d_status;
+
+typedef enum { B200D_PARITY = 0, B200D_FAST = 1 } b200d_arith;
+
+/* Camera block, fp32, exactly what the reference uploads per reference view
+ * (mvs_patchmatch.py:237-257, dense_stereo.py:232-259): K = K_scaled cast to fp32,
+ * Kinv = fp32 inverse of K (torch.inverse on the host), R/t world->camera. */
+typedef struct {
+    float K[9];
+    float Kinv[9];
+    float R_ref[9];
+    float t_ref[3];
+    int32_t n_src;
+    float R_src[B200D_MAX_SRC][9];
+    float t_src[B200D_MAX_SRC][3];
+} b200d_cams;
+
+/* Random numbers for PatchMatch.  Either injected tensors (parity tests: the reference's own
+ * torch.rand / torch.randn draws, call order of mvs_patchmatch.py:271,279-280,471,475) or a
+ * counter-based Philox4x32-10 stream keyed by (seed, view, evaluation, pixel). */
+typedef struct {
+    uint64_t seed;               /* used when the matching pointer is NULL */
+    uint32_t view_id;
+    const float *d_init_depth;   /* (H,W)   injected initial depth, or NULL */
+    const float *d_init_normal;  /* (H,W,3) injected initial normal, or NULL */
+    const float *d_rand_u;       /* (iters*samples,H,W)   uniform [0,1) draws, or NULL */
+    const float *d_rand_n;       /* (iters*samples,H,W,3) standard normal draws, or NULL */
+} b200d_rng;
+
+/* PatchMatch parameters (PatchMatchMVS.__init__, mvs_patchmatch.py:43-59). */
+typedef struct {
+    int32_t patch;               /* odd NCC window: 3,5,7,9,11,13 */
+    int32_t iters;
+    int32_t samples;
+    int32_t arith;               /* b200d_arith */
+    /* f64 like the Python attributes: the per-iteration ranges (dmax-dmin)*0.5^it and 0.5*0.5^it
+     * are evaluated in double and then cast to fp32 (mvs_patchmatch.py:466-467); clamp and border
+     * fill use the fp32 casts. */
+    double depth_min, depth_max;
+} b200d_pm_params;
+
+/* Scratch for one PatchMatch view: ping-pong state + reference window statistics.
+ * b200d_pm_scratch_bytes(H,W) bytes of device memory, 256-byte aligned. */
+B200D_API size_t b200d_pm_scratch_bytes(int H, int W);
+
+B200D_API int b200d_abi_version(void);
+B200D_API const char *b200d_last_error(void);
+B200D_API int b200d_device_count(void);
+
+/* Reference-side window statistics mean1 = box(r), var1 = box(r*r) - mean1^2
+ * (first two conv2d of _ncc_cost / _compute_ncc_torch, mvs_patchmatch.py:403-406,
+ * dense_stereo.py:333-337; constant per reference view). */
+B200D_API int b200d_ref_stats(const float *d_ref, int H, int W, int patch, float *d_mean1, float *d_var1, void *stream);
+
+/* Replaces PatchMatchMVS._compute_patch_cost (mvs_patchmatch.py:323-390) when mode==0 and
+ * PatchMatchMVS._compute_confidence (:493-534) when mode==1, for a given per-pixel depth map.
+ * d_src[s] are the source grays (H,W) fp32.  d_mean1/d_var1 from b200d_ref_stats. */
+B200D_API int b200d_pm_cost(const float *d_ref, const float *d_mean1, const float *d_var1,
+                  const float *const *d_src, const b200d_cams *cams, const float *d_depth,
+                  int H, int W, int patch, int mode, int arith, float *d_out, void *stream);
+
+/* Replaces PatchMatchMVS._patchmatch_cuda (mvs_patchmatch.py:225-321) from initialisation to the
+ * confidence map: init -> iters x (2 shifted-neighbour evaluations + `samples` random
+ * refinements, strict `<` selection) -> confidence.  Results: d_depth (H,W), d_normal (H,W,3),
+ * d_conf (H,W), optional d_best (H,W).  d_costs (iters*(2+samples),H,W) optional dump of every
+ * evaluated cost map (tests). */
+B200D_API int b200d_pm_view(const float *d_ref, const float *const *d_src, const b200d_cams *cams,
+                  int H, int W, const b200d_pm_params *prm, const b200d_rng *rng,
+                  void *d_scratch, float *d_depth, float *d_normal, float *d_conf, float *d_best,
+                  float *d_costs, void *stream);
+
+/* Replaces DenseStereoReconstructor._plane_sweep_torch (dense_stereo.py:222-316):
+ * for each plane d (given order) and neighbour n: reproject at constant depth, bilinear sample,
+ * box NCC (_compute_ncc_torch :318-347), count (ncc > thresh) & (z > 0.1); first arg-max over d.
+ * d_depths (D) fp32.  Outputs d_depth_map, d_conf (H,W) fp32, d_idx (H,W) int32;
+ * d_ncc (D,N,H,W) optional dump of the NCC volume (tests).
+ * d_scratch: b200d_sweep_scratch_bytes(H,W) bytes (reference window statistics). */
+B200D_API size_t b200d_sweep_scratch_bytes(int H, int W);
+B200D_API int b200d_plane_sweep(const float *d_ref, const float *const *d_nbr, const b200d_cams *cams,
+                      const float *d_depths, int D, int H, int W, int patch, float thresh, int arith,
+                      float *d_depth_map, float *d_conf, int32_t *d_idx, float *d_ncc, void *d_scratch,
+                      void *stream);
+
+/* Replaces the per-view body of PatchMatchMVS._fuse_depth_maps (mvs_patchmatch.py:545-565, mode 0:
+ * valid = conf >= min_conf) and DenseStereoReconstructor._backproject (dense_stereo.py:414-437,
+ * mode 1: valid = conf >= min_conf && depth > 0): mask, row-major ordered compaction,
+ * back-projection X = ((Kinv [x,y,1]) d - t) R in f64, colour BGR->RGB.
+ * Kinv64/R64/t64 are HOST f64.  d_points (>= H*W*3 f64), d_colors (>= H*W*3 u8),
+ * d_count (1 x int64), d_scratch: b200d_fuse_scratch_bytes(H,W) bytes. */
+B200D_API size_t b200d_fuse_scratch_bytes(int H, int W);
+B200D_API int b200d_mask_backproject(const float *d_depth, const float *d_conf, const uint8_t *d_bgr, int H, int W,
+                           const double *Kinv64, const double *R64, const double *t64,
+                           float min_conf, int mode, double *d_points, uint8_t *d_colors,
+                           int64_t *d_count, void *d_scratch, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DENSE_H */

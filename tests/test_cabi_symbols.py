@@ -1,0 +1,61 @@
+"""CPU: the C-ABI library loads and exports every symbol include/b200dense.h declares.
+No compute call is made (no GPU here); argument validation paths that do not touch CUDA are checked."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from b200dense import _cabi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, 'include', 'b200dense.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(b200d_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_built():
+    assert os.path.exists(_cabi.LIB_PATH), 'run python 3d-reconstruction-tool_b200/csrc/build.py'
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = _cabi.load()
+    syms = header_symbols()
+    assert len(syms) >= 10
+    for s in syms:
+        assert hasattr(lib, s), f'{s} declared in include/b200dense.h but not exported'
+        assert s in _cabi.PROTOTYPES, f'{s} has no ctypes prototype'
+    assert sorted(_cabi.PROTOTYPES) == syms
+
+
+def test_abi_version_and_struct_layout():
+    lib = _cabi.load()
+    assert lib.b200d_abi_version() == 1
+    # b200d_cams: 9+9+9+3 floats, int32, 8*9 + 8*3 floats
+    assert C.sizeof(_cabi.Cams) == 4 * (30 + 1 + 72 + 24)
+    assert C.sizeof(_cabi.PmParams) == 4 * 4 + 2 * 8
+    assert lib.b200d_pm_scratch_bytes(1200, 1600) >= 12 * 1200 * 1600 * 4
+    assert lib.b200d_sweep_scratch_bytes(10, 10) == 800
+    assert lib.b200d_fuse_scratch_bytes(10, 10) > 0
+
+
+def test_argument_errors_do_not_touch_cuda():
+    lib = _cabi.load()
+    rc = lib.b200d_ref_stats(None, 10, 10, 4, None, None, None)     # even patch
+    assert rc == -1 and b'patch' in lib.b200d_last_error()
+    rc = lib.b200d_ref_stats(None, 10, 10, 5, None, None, None)     # null pointers
+    assert rc == -1 and b'null' in lib.b200d_last_error()
+    with pytest.raises(_cabi.B200DenseError):
+        _cabi.check(rc)
+
+
+def test_engine_refuses_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    from b200dense.engine import DenseEngine
+    with pytest.raises(_cabi.B200DenseError):
+        DenseEngine('cuda:0')
