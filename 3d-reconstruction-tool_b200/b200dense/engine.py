@@ -84,6 +84,31 @@ class DenseEngine:
         t = torch.from_numpy(np.ascontiguousarray(a))
         return t.to(self.device, dtype=dtype, non_blocking=True).contiguous()
 
+    @staticmethod
+    def to_host(ts: Sequence[torch.Tensor]) -> List[np.ndarray]:
+        """Device tensors -> fresh host arrays through pinned staging (torch's caching host allocator
+        recycles the pinned blocks, so this is one DMA per tensor and one synchronisation in total)."""
+        hs = []
+        for t in ts:
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            hs.append(h)
+        torch.cuda.current_stream().synchronize()
+        return [h.numpy() for h in hs]
+
+    # ------------------------------------------------------------------ per-launch timing (benchmarks)
+    def profile_begin(self, max_records: int = 65536) -> None:
+        _cabi.check(self.lib.b200d_profile_begin(int(max_records)))
+
+    def profile_end(self, cap: int = 65536):
+        """-> (durations_ms float32[n], tags int32[n]) of the kernels launched since profile_begin."""
+        ms = np.zeros(cap, np.float32)
+        tags = np.zeros(cap, np.int32)
+        n = C.c_int(0)
+        _cabi.check(self.lib.b200d_profile_end(ms.ctypes.data_as(C.POINTER(C.c_float)),
+                                               tags.ctypes.data_as(C.POINTER(C.c_int32)), cap, C.byref(n)))
+        return ms[:n.value], tags[:n.value]
+
     # ------------------------------------------------------------------ entry points
     def ref_stats(self, ref: torch.Tensor, patch: int) -> Tuple[torch.Tensor, torch.Tensor]:
         H, W = ref.shape
@@ -149,9 +174,11 @@ class DenseEngine:
 
     def mask_backproject(self, depth: torch.Tensor, conf: torch.Tensor, bgr: torch.Tensor, Kinv64: np.ndarray,
                          R: np.ndarray, t: np.ndarray, min_conf: float, mode: int,
-                         points: Optional[torch.Tensor] = None, colors: Optional[torch.Tensor] = None):
+                         points: Optional[torch.Tensor] = None, colors: Optional[torch.Tensor] = None,
+                         sync: bool = True):
         """Mask + ordered compaction + back-projection (mvs_patchmatch.py:545-565 / dense_stereo.py:414-437).
-        Returns (points (M,3) f64, colors (M,3) u8) device tensors; synchronises to read M."""
+        Returns (points (M,3) f64, colors (M,3) u8) device tensors; synchronises to read M.
+        With sync=False nothing is read back: returns (points buffer, colors buffer, count tensor)."""
         H, W = depth.shape
         if points is None:
             points = torch.empty((H * W, 3), dtype=torch.float64, device=self.device)
@@ -167,5 +194,7 @@ class DenseEngine:
                                                     _ptr(points), _ptr(colors), _ptr(count),
                                                     _ptr(self.scratch('fuse', H, W)), self._stream()))
         self.launches += 3
+        if not sync:
+            return points, colors, count
         m = int(count.item())
         return points[:m], colors[:m]

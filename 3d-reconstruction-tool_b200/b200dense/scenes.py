@@ -36,7 +36,7 @@ class Scene:
 
     @property
     def shape(self) -> Tuple[int, int]:
-        return self.images[0]['image'].shape[:2]
+        return next(im for im in self.images if im is not None)['image'].shape[:2]
 
 
 def make_texture(seed: int = 0, size: int = 2048, sigma: float = 1.5) -> torch.Tensor:
@@ -97,7 +97,7 @@ def _rays(K: np.ndarray, R: np.ndarray, H: int, W: int, device) -> Tuple[torch.T
 
 def make_scene(kind: str = 'plane', n_views: int = 5, width: int = 640, height: int = 480,
                focal: float = None, arc_deg: float = 8.0, seed: int = 0,
-               device: str = 'cpu', radius: float = 5.0) -> Scene:
+               device: str = 'cpu', radius: float = 5.0, render=None) -> Scene:
     """Build a synthetic multi-view scene.
 
     ``plane``     : textured plane z=5, cameras on an arc of ``arc_deg`` per step around it.
@@ -105,6 +105,8 @@ def make_scene(kind: str = 'plane', n_views: int = 5, width: int = 640, height: 
     ``turntable`` : textured unit-ish sphere (r=1.5) inside a large textured shell (r=12),
                     cameras on a full circle of ``radius`` looking at the origin,
                     ``arc_deg`` between neighbouring views.
+    ``render``: optional iterable of view indices to rasterise; the other views get poses only
+    (their ``images`` / ``depth_gt`` entries are None) -- large benchmark scenes render what a rank needs.
     """
     W, H = int(width), int(height)
     f = float(focal) if focal is not None else 0.9 * W
@@ -130,6 +132,10 @@ def make_scene(kind: str = 'plane', n_views: int = 5, width: int = 640, height: 
             raise ValueError(f"unknown scene kind {kind!r}")
         R, t = look_at_pose(C, target)
         poses[i] = (R, t)
+        if render is not None and i not in render:
+            images.append(None)
+            depth_gt.append(None)
+            continue
 
         dw, _ = _rays(K, R, H, W, dev)
         Ct = torch.from_numpy(C).to(dev)
@@ -182,4 +188,5 @@ def gray_f32(scene: Scene) -> List[np.ndarray]:
     """Working-resolution grayscale in [0,1] f32, computed like the reference's
     `_prepare_images` at scale 1.0 (`mvs_patchmatch.py:176-177`): OpenCV BGR2GRAY then /255."""
     import cv2 as cv
-    return [cv.cvtColor(im['image'], cv.COLOR_BGR2GRAY).astype(np.float32) / 255.0 for im in scene.images]
+    return [None if im is None else cv.cvtColor(im['image'], cv.COLOR_BGR2GRAY).astype(np.float32) / 255.0
+            for im in scene.images]

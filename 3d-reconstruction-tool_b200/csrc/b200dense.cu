@@ -3,6 +3,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "b200dense.h"
 #include "fuse_kernels.cuh"
@@ -34,6 +36,31 @@ int cuda_check(cudaError_t e, const char *what) {
 
 size_t align256(size_t n) { return (n + 255) / 256 * 256; }
 
+// ---- optional per-launch timing (b200d_profile_begin/_end): CUDA events recorded on the launching
+// stream around every tile kernel, so a benchmark can report the dominant kernel's own duration.
+struct ProfRec { cudaEvent_t e0, e1; int tag; };
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;
+size_t g_prof_used = 0;
+bool g_prof_on = false;
+
+struct ProfScope {
+    ProfRec *r = nullptr;
+    cudaStream_t st;
+    ProfScope(int tag, cudaStream_t s) : st(s) {
+        if (!g_prof_on) return;
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        if (g_prof_used < g_prof.size()) {
+            r = &g_prof[g_prof_used++];
+            r->tag = tag;
+            cudaEventRecord(r->e0, st);
+        }
+    }
+    ~ProfScope() {
+        if (r) cudaEventRecord(r->e1, st);
+    }
+};
+
 dim3 tile_grid(int H, int W) { return dim3((W + TW - 1) / TW, (H + TH - 1) / TH, 1); }
 
 template <int K, int MODE>
@@ -44,6 +71,7 @@ int launch_pm(const PmArgs &a, cudaStream_t st) {
                                       (int)Geo<K>::smem_bytes));
         configured = true;
     }
+    ProfScope prof(MODE * 100 + K, st);
     pm_eval_kernel<K, MODE><<<tile_grid(a.H, a.W), NT, Geo<K>::smem_bytes, st>>>(a);
     return cuda_check(cudaGetLastError(), "pm_eval_kernel launch");
 }
@@ -69,6 +97,7 @@ int launch_sweep(const SweepArgs &a, cudaStream_t st) {
         CUDA_TRY(cudaFuncSetAttribute(plane_sweep_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
+    ProfScope prof(1000 + K, st);
     plane_sweep_kernel<K><<<tile_grid(a.H, a.W), NT, smem, st>>>(a);
     return cuda_check(cudaGetLastError(), "plane_sweep_kernel launch");
 }
@@ -123,6 +152,37 @@ int b200d_device_count(void) {
         return 0;
     }
     return n;
+}
+
+int b200d_profile_begin(int max_records) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (max_records < 1 || max_records > (1 << 20)) return fail(B200D_ERR_ARG, "max_records out of range%s");
+    for (auto &r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    g_prof.assign((size_t)max_records, ProfRec{});
+    for (auto &r : g_prof) {
+        CUDA_TRY(cudaEventCreate(&r.e0));
+        CUDA_TRY(cudaEventCreate(&r.e1));
+    }
+    g_prof_used = 0;
+    g_prof_on = true;
+    return B200D_OK;
+}
+
+int b200d_profile_end(float *ms_out, int32_t *tag_out, int cap, int *n_out) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = false;
+    int n = 0, rc = B200D_OK;
+    for (size_t i = 0; i < g_prof_used && rc == B200D_OK; ++i) {
+        float ms = 0.f;
+        rc = cuda_check(cudaEventSynchronize(g_prof[i].e1), "cudaEventSynchronize");
+        if (rc == B200D_OK) rc = cuda_check(cudaEventElapsedTime(&ms, g_prof[i].e0, g_prof[i].e1), "cudaEventElapsedTime");
+        if (rc == B200D_OK && n < cap && ms_out && tag_out) { ms_out[n] = ms; tag_out[n] = g_prof[i].tag; ++n; }
+    }
+    for (auto &r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    g_prof.clear();
+    g_prof_used = 0;
+    if (n_out) *n_out = n;
+    return rc;
 }
 
 size_t b200d_pm_scratch_bytes(int H, int W) {

@@ -1,0 +1,213 @@
+"""Plane-sweep dense stereo -- drop-in for the reference's `core.dense_stereo`
+(reference: src/core/dense_stereo.py), computed by hand-written sm_100a kernels.
+
+Same class / function names, constructor keywords, `reconstruct` signature, return types,
+stdout banners and empty-result conventions as the reference.  The (plane x neighbour) loop that
+the reference runs as ~45 eager PyTorch kernels per iteration is one kernel launch per reference
+view here (b200d_plane_sweep); masking + back-projection is b200d_mask_backproject.
+No CPU fallback: without a CUDA device the compute methods raise B200DenseError (the reference's
+`_plane_sweep_numpy` SSD fallback computes a different metric and is not reproduced).
+"""
+from __future__ import annotations
+
+import time
+from typing import Dict, List, Tuple
+
+import cv2 as cv
+import numpy as np
+import torch
+
+from .camera import Camera, CameraPose
+
+
+class DenseStereoReconstructor:
+    def __init__(self, camera: Camera, scale: float = 0.25, num_depths: int = 64, patch_size: int = 5,
+                 min_views: int = 3, consistency_thresh: float = 0.8, *, num_neighbors: int = 6, device=None):
+        self.camera = camera
+        self.scale = scale
+        self.num_depths = num_depths
+        self.patch_size = patch_size
+        self.min_views = min_views
+        self.consistency_thresh = consistency_thresh
+        self.num_neighbors = num_neighbors
+        self.device = torch.device(device) if device is not None else torch.device('cuda')
+        self._engine = None
+        self._dev_gray: Dict[int, Tuple[int, torch.Tensor]] = {}
+        if torch.cuda.is_available():
+            print(f"Dense stereo using GPU: {torch.cuda.get_device_name()}")
+        else:
+            print("Dense stereo: no CUDA device visible (compute calls will raise; there is no CPU path)")
+        # reference :55-59 scales fx, fy, cx, cy
+        self.K_scaled = camera.K.copy()
+        for r, c in ((0, 0), (1, 1), (0, 2), (1, 2)):
+            self.K_scaled[r, c] *= scale
+
+    @property
+    def engine(self):
+        if self._engine is None:
+            from b200dense.engine import DenseEngine
+            self._engine = DenseEngine(self.device)
+        return self._engine
+
+    def _gray_on_device(self, processed: Dict, idx: int) -> torch.Tensor:
+        g = processed[idx]['gray']
+        hit = self._dev_gray.get(idx)
+        if hit is not None and hit[0] == id(g):
+            return hit[1]
+        t = self.engine.to_device(g)
+        self._dev_gray[idx] = (id(g), t)
+        return t
+
+    # ------------------------------------------------------------------ public API
+    def reconstruct(self, images: List[dict], poses: Dict[int, CameraPose],
+                    max_pairs: int = 30) -> Tuple[np.ndarray, np.ndarray]:
+        """Dense cloud from a subset of reference views (reference :61-154)."""
+        print("\n" + "=" * 60)
+        print("GPU DENSE STEREO")
+        print(f"  Scale: {self.scale}x, Depths: {self.num_depths}, Min views: {self.min_views}")
+        print("=" * 60)
+        t0 = time.time()
+        camera_indices = sorted(poses.keys())
+        n_cameras = len(camera_indices)
+        if n_cameras < 3:
+            print("Need at least 3 cameras for multi-view stereo")
+            return np.array([]), np.array([])
+
+        print("\nPreparing images...")
+        processed = self._prepare_images(images, camera_indices)
+        self._dev_gray.clear()
+
+        depth_min, depth_max = self._depth_range(poses, camera_indices)
+        print(f"  Depth range: {depth_min:.2f} - {depth_max:.2f}")
+
+        step = max(1, n_cameras // max_pairs)                    # reference :100-101
+        ref_indices = camera_indices[::step]
+        print(f"\nProcessing {len(ref_indices)} reference views...")
+        all_points, all_colors = [], []
+        for i, ref_idx in enumerate(ref_indices):
+            t1 = time.time()
+            neighbors = self._find_neighbors(ref_idx, camera_indices, poses, k=self.num_neighbors)
+            if len(neighbors) < 2:
+                continue
+            depth_map, confidence, color_map = self._compute_depth_map_gpu(
+                ref_idx, neighbors, processed, poses, depth_min, depth_max)
+            points, colors = self._backproject(depth_map, confidence, color_map, poses[ref_idx],
+                                               min_confidence=self.min_views - 0.5)
+            if len(points) > 0:
+                all_points.append(points)
+                all_colors.append(colors)
+            print(f"  [{i+1}/{len(ref_indices)}] Cam {ref_idx}: {len(points):,} pts ({time.time() - t1:.1f}s)")
+
+        if not all_points:
+            print("No points reconstructed!")
+            return np.array([]), np.array([])
+        print("\nMerging point clouds...")
+        points, colors = np.vstack(all_points), np.vstack(all_colors)
+        print(f"  Raw points: {len(points):,}")
+        points, colors = self._filter_outliers(points, colors)
+        print(f"  After outlier removal: {len(points):,}")
+        points, colors = self._voxel_down_sample(points, colors, voxel_size=0.02)
+        print(f"  After voxel downsample: {len(points):,}")
+        print(f"\nDense stereo completed in {time.time() - t0:.1f}s")
+        return points, colors
+
+    # ------------------------------------------------------------------ host heuristics
+    @staticmethod
+    def _depth_range(poses, camera_indices) -> Tuple[float, float]:
+        """[max(0.1, 0.1 r), 5 r], r = 90th percentile of camera distance to the median centre (:86-91)."""
+        centers = np.array([poses[i].center for i in camera_indices])
+        r = np.percentile(np.linalg.norm(centers - np.median(centers, axis=0), axis=1), 90)
+        return max(0.1, r * 0.1), r * 5.0
+
+    def _prepare_images(self, images: List[dict], indices: List[int]) -> Dict:
+        out = {}
+        for idx in indices:
+            img = images[idx]['image']
+            h, w = img.shape[:2]
+            nh, nw = int(h * self.scale), int(w * self.scale)
+            small = cv.resize(img, (nw, nh))
+            out[idx] = {'gray': cv.cvtColor(small, cv.COLOR_BGR2GRAY).astype(np.float32) / 255.0,
+                        'color': small, 'shape': (nh, nw)}
+        return out
+
+    def _find_neighbors(self, ref_idx: int, all_indices: List[int], poses: Dict[int, CameraPose],
+                        k: int = 6) -> List[int]:
+        """k nearest camera centres, ties in index order (reference :178-191)."""
+        c0 = poses[ref_idx].center
+        d = [(i, np.linalg.norm(poses[i].center - c0)) for i in all_indices if i != ref_idx]
+        d.sort(key=lambda p: p[1])
+        return [i for i, _ in d[:k]]
+
+    # ------------------------------------------------------------------ device path
+    def _plane_depths(self, depth_min: float, depth_max: float) -> np.ndarray:
+        """Far-to-near planes, uniform in inverse depth (reference :204-205), f64."""
+        return 1.0 / np.linspace(1 / depth_max, 1 / depth_min, self.num_depths)
+
+    def _compute_depth_map_gpu(self, ref_idx: int, neighbor_indices: List[int], processed: Dict,
+                               poses: Dict[int, CameraPose], depth_min: float,
+                               depth_max: float) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """(depth_map, confidence = max consistent-view count, colour) -- reference :193-316."""
+        out = self._sweep_device(ref_idx, neighbor_indices, processed, poses, depth_min, depth_max)
+        return out['depth_map'].cpu().numpy(), out['confidence'].cpu().numpy(), processed[ref_idx]['color']
+
+    def _sweep_device(self, ref_idx, neighbor_indices, processed, poses, depth_min, depth_max) -> dict:
+        from b200dense.engine import kinv32, make_cams
+        eng = self.engine
+        cams = make_cams(self.K_scaled, kinv32(self.K_scaled), poses[ref_idx].R, poses[ref_idx].t,
+                         [poses[i].R for i in neighbor_indices], [poses[i].t for i in neighbor_indices])
+        depths = eng.to_device(self._plane_depths(depth_min, depth_max).astype(np.float32))
+        return eng.plane_sweep(self._gray_on_device(processed, ref_idx),
+                               [self._gray_on_device(processed, i) for i in neighbor_indices], cams, depths,
+                               self.patch_size, self.consistency_thresh)
+
+    def _backproject(self, depth_map: np.ndarray, confidence: np.ndarray, color_map: np.ndarray,
+                     pose: CameraPose, min_confidence: float) -> Tuple[np.ndarray, np.ndarray]:
+        """valid = (conf >= min_confidence) & (depth > 0), row-major order (reference :407-437)."""
+        eng = self.engine
+        pts, cols = eng.mask_backproject(eng.to_device(depth_map), eng.to_device(confidence),
+                                         eng.to_device(color_map, torch.uint8), np.linalg.inv(self.K_scaled),
+                                         pose.R, pose.t, float(min_confidence), 1)
+        if pts.shape[0] == 0:
+            return np.array([]).reshape(0, 3), np.array([]).reshape(0, 3)
+        return pts.cpu().numpy(), cols.cpu().numpy()
+
+    # ------------------------------------------------------------------ host post-filters
+    def _filter_outliers(self, points: np.ndarray, colors: np.ndarray, k: int = 20,
+                         std_ratio: float = 2.0) -> Tuple[np.ndarray, np.ndarray]:
+        """k-NN statistical outlier removal, threshold mean + std_ratio * std (reference :439-473).
+        Above 500k points the reference subsamples with an unseeded np.random.choice; so does this."""
+        if len(points) < k + 1:
+            return points, colors
+        try:
+            from sklearn.neighbors import NearestNeighbors
+        except ImportError:
+            dist = np.linalg.norm(points - np.median(points, axis=0), axis=1)
+            keep = dist < np.percentile(dist, 95)
+            return points[keep], colors[keep]
+        if len(points) > 500000:
+            indices = np.random.choice(len(points), 500000, replace=False)
+        else:
+            indices = np.arange(len(points))
+        sample = points[indices]
+        dists, _ = NearestNeighbors(n_neighbors=k).fit(sample).kneighbors(sample)
+        mean_d = np.mean(dists[:, 1:], axis=1)
+        inlier = mean_d < np.mean(mean_d) + std_ratio * np.std(mean_d)
+        return points[indices[inlier]], colors[indices[inlier]]
+
+    def _voxel_down_sample(self, points: np.ndarray, colors: np.ndarray,
+                           voxel_size: float) -> Tuple[np.ndarray, np.ndarray]:
+        """First point of every voxel, ordered by voxel key (reference :475-492)."""
+        if len(points) == 0:
+            return points, colors
+        v = np.floor(points / voxel_size).astype(np.int32).astype(np.int64)
+        keys = v[:, 0] * 1000000000 + v[:, 1] * 1000000 + v[:, 2]
+        _, first = np.unique(keys, return_index=True)
+        return points[first], colors[first]
+
+
+def create_combined_dense_cloud(camera: Camera, images: List[dict], poses: Dict[int, CameraPose],
+                                use_stereo: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+    """Reference :495-505."""
+    if not use_stereo:
+        return np.array([]), np.array([])
+    return DenseStereoReconstructor(camera).reconstruct(images, poses)

@@ -143,6 +143,14 @@ B200D_API int b200d_mask_backproject(const float *d_depth, const float *d_conf, 
                            float min_conf, int mode, double *d_points, uint8_t *d_colors,
                            int64_t *d_count, void *d_scratch, void *stream);
 
+/* Optional per-launch timing for benchmarks.  Between _begin and _end every tile kernel launched by
+ * this library is bracketed by CUDA events on its own stream (library-owned events, at most
+ * max_records launches).  _end waits for the recorded launches, writes their durations (ms) and tags
+ * (PatchMatch kernels: mode*100 + patch with mode 0 stats, 1 cost, 2 confidence, 3 shift, 4 refine;
+ * plane sweep: 1000 + patch) and releases the events.  Not meant to be left on in production. */
+B200D_API int b200d_profile_begin(int max_records);
+B200D_API int b200d_profile_end(float *ms_out, int32_t *tag_out, int cap, int *n_out);
+
 #ifdef __cplusplus
 }
 #endif
