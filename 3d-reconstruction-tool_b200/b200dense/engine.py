@@ -62,6 +62,8 @@ class DenseEngine:
         self.device = torch.device(device if not isinstance(device, int) else f'cuda:{device}')
         if self.device.type != 'cuda':
             raise B200DenseError(f"DenseEngine needs a CUDA device, got {self.device}")
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
         torch.cuda.set_device(self.device)
         self._scratch: Dict[Tuple[str, int, int], torch.Tensor] = {}
         self.launches = 0                     # kernels of ours enqueued (bench's gpu_launches claim)

@@ -48,29 +48,53 @@ def test_patchmatch_reconstruct_matches_reference(scale):
     np.testing.assert_allclose(p, ep, rtol=0, atol=1e-9)
 
 
-def test_patchmatch_philox_is_deterministic_and_plausible():
-    """Production RNG: same seed -> identical maps; different seed -> different maps; on an easy scene
-    most confident pixels land near the true depth."""
-    from b200dense.scenes import make_scene
+def test_patchmatch_philox_is_deterministic_and_statistically_like_injected():
+    """Production RNG (in-kernel Philox): same seed -> identical maps; different seed -> different maps;
+    and the outcome is statistically the same process as the injected-RNG path the parity tests pin:
+    the final depth histogram matches the CPU oracle run with an independent NumPy stream.
+    (The reference's schedule converges weakly on this scene -- SURVEY 7.3 -- so closeness to ground truth
+    is not a property to assert; equality of behaviour is.)"""
+    from b200dense.engine import kinv32
+    from b200dense.scenes import gray_f32, make_scene
+    from oracle import oracle as orc
     sc = make_scene('plane', 5, 192, 144, seed=8)
     cam = Camera(K=sc.K.copy(), dist=np.zeros(5))
     poses = {i: CameraPose(R=sc.poses[i][0], t=sc.poses[i][1]) for i in sc.poses}
+    ref, src = 2, [1, 3, 0, 4]
     out = []
     for seed in (1, 1, 2):
         pm = PatchMatchMVS(cam, scale=1.0, patch_size=7, num_iterations=3, num_samples=8, seed=seed)
         pm.depth_min, pm.depth_max = sc.depth_range
         proc = pm._prepare_images(sc.images, sorted(poses))
-        out.append(pm._patchmatch_cuda(2, [1, 3, 0, 4], proc, poses))
+        out.append(pm._patchmatch_cuda(ref, src, proc, poses))
     assert np.array_equal(out[0].depth, out[1].depth) and np.array_equal(out[0].normal, out[1].normal)
+    assert np.array_equal(out[0].confidence, out[1].confidence)
     assert not np.array_equal(out[0].depth, out[2].depth)
     d = out[0]
-    assert np.isfinite(d.depth).all() and d.depth.min() >= sc.depth_range[0] and d.depth.max() <= sc.depth_range[1]
+    dmin, dmax = sc.depth_range
+    assert np.isfinite(d.depth).all() and d.depth.min() >= np.float32(dmin) and d.depth.max() <= np.float32(dmax)
     nrm = np.linalg.norm(d.normal, axis=-1)
     assert np.all((np.abs(nrm - 1) < 1e-5) | (nrm == 0))
-    conf = d.confidence >= 3
-    assert conf.sum() > 100
-    rel = np.abs(d.depth[conf] - sc.depth_gt[2][conf]) / sc.depth_gt[2][conf]
-    assert np.median(rel) < 0.05
+    assert set(np.unique(d.confidence)) <= {0.0, 1.0, 2.0, 3.0, 4.0}
+
+    g = gray_f32(sc)
+    H, W = g[0].shape
+    rng = np.random.default_rng(1)
+    n = 24
+    d0 = np.exp(rng.random((H, W), dtype=np.float32) * np.float32(np.log(dmax / dmin)) + np.float32(np.log(dmin)))
+    n0 = rng.standard_normal((H, W, 3), dtype=np.float32) * np.float32(0.3)
+    n0[..., 2] = -1
+    n0 /= np.linalg.norm(n0, axis=-1, keepdims=True)
+    cams = orc.Cams(sc.K, kinv32(sc.K), poses[ref].R, poses[ref].t, [poses[i].R for i in src], [poses[i].t for i in src])
+    o = orc.pm_view(g[ref], [g[i] for i in src], cams, 7, 3, 8, dmin, dmax, d0, n0,
+                    rng.random((n, H, W), dtype=np.float32), rng.standard_normal((n, H, W, 3), dtype=np.float32))
+    bins = [dmin, dmin * 1.00001, 3, 4, 4.75, 5.25, 6, 8, dmax * 1.00001]
+    hg = np.histogram(d.depth, bins=bins)[0] / d.depth.size
+    ho = np.histogram(o['depth'], bins=bins)[0] / d.depth.size
+    assert np.abs(hg - ho).max() < 0.03, (hg, ho)
+    cg = np.bincount(d.confidence.astype(int).ravel(), minlength=5) / d.depth.size
+    co = np.bincount(o['confidence'].astype(int).ravel(), minlength=5) / d.depth.size
+    assert np.abs(cg - co).max() < 0.03, (cg, co)
 
 
 def test_fewer_than_two_neighbours_skips_view_and_wrapper():
