@@ -41,14 +41,13 @@ PROTOTYPES = {
     'b200d_abi_version': (C.c_int, []),
     'b200d_last_error': (C.c_char_p, []),
     'b200d_device_count': (C.c_int, []),
-    'b200d_pm_scratch_bytes': (C.c_size_t, [_i, _i]),
-    'b200d_sweep_scratch_bytes': (C.c_size_t, [_i, _i]),
+    'b200d_scratch_bytes': (C.c_size_t, [_i, _i]),
     'b200d_fuse_scratch_bytes': (C.c_size_t, [_i, _i]),
-    'b200d_ref_stats': (C.c_int, [_vp, _i, _i, _i, _vp, _vp, _vp]),
-    'b200d_pm_cost': (C.c_int, [_vp, _vp, _vp, C.POINTER(_vp), C.POINTER(Cams), _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    'b200d_ref_stats': (C.c_int, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    'b200d_pm_cost': (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(Cams), _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     'b200d_pm_view': (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(Cams), _i, _i, C.POINTER(PmParams), C.POINTER(Rng),
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    'b200d_plane_sweep': (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(Cams), _vp, _i, _i, _i, _i, _f, _i,
+    'b200d_plane_sweep': (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(Cams), C.POINTER(C.c_float), _i, _i, _i, _i, _f, _i,
                                     _vp, _vp, _vp, _vp, _vp, _vp]),
     'b200d_profile_begin': (C.c_int, [_i]),
     'b200d_profile_end': (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32), _i, C.POINTER(C.c_int)]),

@@ -65,19 +65,19 @@ class DenseEngine:
         if self.device.index is None:
             self.device = torch.device('cuda', torch.cuda.current_device())
         torch.cuda.set_device(self.device)
-        self._scratch: Dict[Tuple[str, int, int], torch.Tensor] = {}
+        self._scratch: Dict[Tuple[str, int, int, int], torch.Tensor] = {}
+        self._streams: List[torch.cuda.Stream] = []
         self.launches = 0                     # kernels of ours enqueued (bench's gpu_launches claim)
 
     # ------------------------------------------------------------------ helpers
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def scratch(self, kind: str, H: int, W: int) -> torch.Tensor:
-        key = (kind, H, W)
+    def scratch(self, kind: str, H: int, W: int, slot: int = 0) -> torch.Tensor:
+        key = (kind, H, W, slot)
         buf = self._scratch.get(key)
         if buf is None:
-            nbytes = {'pm': self.lib.b200d_pm_scratch_bytes, 'sweep': self.lib.b200d_sweep_scratch_bytes,
-                      'fuse': self.lib.b200d_fuse_scratch_bytes}[kind](H, W)
+            nbytes = {'view': self.lib.b200d_scratch_bytes, 'fuse': self.lib.b200d_fuse_scratch_bytes}[kind](H, W)
             buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
             self._scratch[key] = buf
         return buf
@@ -98,6 +98,34 @@ class DenseEngine:
         torch.cuda.current_stream().synchronize()
         return [h.numpy() for h in hs]
 
+    # ------------------------------------------------------------------ concurrent views
+    def run_views(self, jobs: Sequence, n_streams: int = 4) -> list:
+        """Run independent per-view jobs concurrently on `n_streams` side streams.
+
+        A reference view's PatchMatch is a chain of ~33 dependent launches whose grids (950 CTAs at
+        1600x1200) leave a partly empty last wave on 148 SMs; views are independent, so the
+        tail of one view's launch is filled by another view's.  `jobs` are callables taking the slot
+        index (their scratch slot); job j runs on stream j % n_streams, i.e. jobs sharing a slot are
+        serialised.  The caller's current stream waits for all of them before this returns."""
+        n = max(1, min(n_streams, len(jobs)))
+        while len(self._streams) < n:
+            self._streams.append(torch.cuda.Stream(device=self.device))
+        main = torch.cuda.current_stream(self.device)
+        start = torch.cuda.Event()
+        start.record(main)
+        results = []
+        for j, job in enumerate(jobs):
+            st = self._streams[j % n]
+            if j < n:
+                st.wait_event(start)
+            with torch.cuda.stream(st):
+                results.append(job(j % n))
+        for st in self._streams[:n]:
+            done = torch.cuda.Event()
+            done.record(st)
+            main.wait_event(done)
+        return results
+
     # ------------------------------------------------------------------ per-launch timing (benchmarks)
     def profile_begin(self, max_records: int = 65536) -> None:
         _cabi.check(self.lib.b200d_profile_begin(int(max_records)))
@@ -116,25 +144,27 @@ class DenseEngine:
         H, W = ref.shape
         mean1 = torch.empty_like(ref)
         var1 = torch.empty_like(ref)
-        _cabi.check(self.lib.b200d_ref_stats(_ptr(ref), H, W, patch, _ptr(mean1), _ptr(var1), self._stream()))
+        _cabi.check(self.lib.b200d_ref_stats(_ptr(ref), H, W, patch, _ptr(mean1), _ptr(var1),
+                                             _ptr(self.scratch('view', H, W)), self._stream()))
         self.launches += 1
         return mean1, var1
 
     def pm_cost(self, ref: torch.Tensor, srcs: Sequence[torch.Tensor], cams: Cams, depth: torch.Tensor, patch: int,
-                mode: int = 0, arith: int = _cabi.PARITY, stats=None) -> torch.Tensor:
+                mode: int = 0, arith: int = _cabi.PARITY) -> torch.Tensor:
+        """Cost map (mode 0, mvs_patchmatch.py:323-390) or confidence count (mode 1, :493-534) of a depth map."""
         H, W = ref.shape
-        mean1, var1 = stats if stats is not None else self.ref_stats(ref, patch)
         out = torch.empty_like(ref)
-        _cabi.check(self.lib.b200d_pm_cost(_ptr(ref), _ptr(mean1), _ptr(var1), _ptr_array(srcs), C.byref(cams),
-                                           _ptr(depth), H, W, patch, mode, arith, _ptr(out), self._stream()))
-        self.launches += 1
+        _cabi.check(self.lib.b200d_pm_cost(_ptr(ref), _ptr_array(srcs), C.byref(cams), _ptr(depth), H, W, patch, mode,
+                                           arith, _ptr(out), _ptr(self.scratch('view', H, W)), self._stream()))
+        self.launches += 3
         return out
 
     def pm_view(self, ref: torch.Tensor, srcs: Sequence[torch.Tensor], cams: Cams, patch: int, iters: int,
                 samples: int, depth_min: float, depth_max: float, *, seed: int = 0, view_id: int = 0,
                 init_depth: Optional[torch.Tensor] = None, init_normal: Optional[torch.Tensor] = None,
                 rand_u: Optional[torch.Tensor] = None, rand_n: Optional[torch.Tensor] = None,
-                arith: int = _cabi.PARITY, dump_costs: bool = False, want_best: bool = False, out=None):
+                arith: int = _cabi.PARITY, dump_costs: bool = False, want_best: bool = False, out=None,
+                slot: int = 0):
         """Full PatchMatch of one reference view (mvs_patchmatch.py:225-321); returns device tensors
         dict(depth, normal, confidence[, best_cost, costs])."""
         H, W = ref.shape
@@ -150,34 +180,37 @@ class DenseEngine:
         costs = (torch.empty((iters * (2 + samples), H, W), dtype=torch.float32, device=self.device)
                  if dump_costs else None)
         _cabi.check(self.lib.b200d_pm_view(_ptr(ref), _ptr_array(srcs), C.byref(cams), H, W, C.byref(prm), C.byref(rng),
-                                           _ptr(self.scratch('pm', H, W)), _ptr(out['depth']), _ptr(out['normal']),
+                                           _ptr(self.scratch('view', H, W, slot)), _ptr(out['depth']), _ptr(out['normal']),
                                            _ptr(out['confidence']), _ptr(best), _ptr(costs), self._stream()))
-        self.launches += 2 + iters * (2 + samples) + 1          # stats, init, evaluations, confidence
+        self.launches += 2 + 2 * (iters * (2 + samples) + 1)    # stats, init, (sample + ncc) per evaluation
         if want_best:
             out['best_cost'] = best
         if dump_costs:
             out['costs'] = costs
         return out
 
-    def plane_sweep(self, ref: torch.Tensor, nbrs: Sequence[torch.Tensor], cams: Cams, depths: torch.Tensor,
-                    patch: int, thresh: float, arith: int = _cabi.PARITY, dump_ncc: bool = False):
-        """Plane sweep of one reference view (dense_stereo.py:222-316); device tensors."""
+    def plane_sweep(self, ref: torch.Tensor, nbrs: Sequence[torch.Tensor], cams: Cams, depths: np.ndarray,
+                    patch: int, thresh: float, arith: int = _cabi.PARITY, dump_ncc: bool = False, slot: int = 0):
+        """Plane sweep of one reference view (dense_stereo.py:222-316); `depths` is a host fp32 array;
+        returns device tensors."""
         H, W = ref.shape
-        D = depths.numel()
+        depths = np.ascontiguousarray(depths, dtype=np.float32)
+        D = int(depths.size)
         depth_map = torch.empty((H, W), dtype=torch.float32, device=self.device)
         conf = torch.empty((H, W), dtype=torch.float32, device=self.device)
         idx = torch.empty((H, W), dtype=torch.int32, device=self.device)
         ncc = torch.empty((D, len(nbrs), H, W), dtype=torch.float32, device=self.device) if dump_ncc else None
-        _cabi.check(self.lib.b200d_plane_sweep(_ptr(ref), _ptr_array(nbrs), C.byref(cams), _ptr(depths), D, H, W, patch,
+        _cabi.check(self.lib.b200d_plane_sweep(_ptr(ref), _ptr_array(nbrs), C.byref(cams),
+                                               depths.ctypes.data_as(C.POINTER(C.c_float)), D, H, W, patch,
                                                float(thresh), arith, _ptr(depth_map), _ptr(conf), _ptr(idx), _ptr(ncc),
-                                               _ptr(self.scratch('sweep', H, W)), self._stream()))
-        self.launches += 2
+                                               _ptr(self.scratch('view', H, W, slot)), self._stream()))
+        self.launches += 1 + 2 * D
         return dict(depth_map=depth_map, confidence=conf, best_idx=idx, ncc=ncc)
 
     def mask_backproject(self, depth: torch.Tensor, conf: torch.Tensor, bgr: torch.Tensor, Kinv64: np.ndarray,
                          R: np.ndarray, t: np.ndarray, min_conf: float, mode: int,
                          points: Optional[torch.Tensor] = None, colors: Optional[torch.Tensor] = None,
-                         sync: bool = True):
+                         sync: bool = True, slot: int = 0):
         """Mask + ordered compaction + back-projection (mvs_patchmatch.py:545-565 / dense_stereo.py:414-437).
         Returns (points (M,3) f64, colors (M,3) u8) device tensors; synchronises to read M.
         With sync=False nothing is read back: returns (points buffer, colors buffer, count tensor)."""
@@ -194,7 +227,7 @@ class DenseEngine:
         _cabi.check(self.lib.b200d_mask_backproject(_ptr(depth), _ptr(conf), _ptr(bgr), H, W, Ki.ctypes.data_as(dp),
                                                     Rm.ctypes.data_as(dp), tv.ctypes.data_as(dp), float(min_conf), mode,
                                                     _ptr(points), _ptr(colors), _ptr(count),
-                                                    _ptr(self.scratch('fuse', H, W)), self._stream()))
+                                                    _ptr(self.scratch('fuse', H, W, slot)), self._stream()))
         self.launches += 3
         if not sync:
             return points, colors, count

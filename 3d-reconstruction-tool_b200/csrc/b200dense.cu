@@ -1,5 +1,10 @@
 // b200dense.cu -- C-ABI entry points (include/b200dense.h) and kernel dispatch.
 // Compile: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false (see build.py).
+//
+// Every cost evaluation is two launches on the caller's stream:
+//   sample_kernel  (sample_kernels.cuh)  candidate depth -> reproject -> bilinear sample, per pixel
+//   ncc_kernel     (ncc_kernels.cuh)     TMA-fed tiles -> K x K window sums (FFMA2) -> NCC -> select
+// The sampled images sit in an L2-sized scratch between the two.
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -8,8 +13,8 @@
 
 #include "b200dense.h"
 #include "fuse_kernels.cuh"
-#include "pm_kernels.cuh"
-#include "sweep_kernels.cuh"
+#include "ncc_kernels.cuh"
+#include "sample_kernels.cuh"
 
 using namespace b200d;
 
@@ -17,8 +22,8 @@ namespace {
 
 thread_local char g_err[512] = "";
 
-int fail(int code, const char *fmt, const char *detail = "") {
-    snprintf(g_err, sizeof(g_err), fmt, detail);
+int fail(int code, const char *msg) {
+    snprintf(g_err, sizeof(g_err), "%s", msg);
     return code;
 }
 
@@ -33,11 +38,16 @@ int cuda_check(cudaError_t e, const char *what) {
         int _rc = cuda_check((expr), #expr);                  \
         if (_rc != B200D_OK) return _rc;                      \
     } while (0)
+#define TRY(expr)                                             \
+    do {                                                      \
+        int _rc = (expr);                                     \
+        if (_rc != B200D_OK) return _rc;                      \
+    } while (0)
 
 size_t align256(size_t n) { return (n + 255) / 256 * 256; }
 
 // ---- optional per-launch timing (b200d_profile_begin/_end): CUDA events recorded on the launching
-// stream around every tile kernel, so a benchmark can report the dominant kernel's own duration.
+// stream around every kernel, so a benchmark can report each kernel's own duration.
 struct ProfRec { cudaEvent_t e0, e1; int tag; };
 std::mutex g_prof_mu;
 std::vector<ProfRec> g_prof;
@@ -61,50 +71,138 @@ struct ProfScope {
     }
 };
 
-dim3 tile_grid(int H, int W) { return dim3((W + TW - 1) / TW, (H + TH - 1) / TH, 1); }
+// ---- scratch layout shared by all entry points (one slot = one view in flight)
+struct Scratch {
+    float *mean1, *var1, *cand, *best, *normal_alt, *rpad, *smap;
+    uint8_t *valid;
+    int Wp;
+    size_t map_stride;           // floats between consecutive sampled maps
+    static int pitch(int W) { return (W + 3 + 3) / 4 * 4; }     // room for the largest column offset (PAD <= 3)
+    static size_t bytes(int H, int W) {
+        const size_t n = (size_t)H * W, np = (size_t)H * pitch(W);
+        return 4 * align256(n * 4) + align256(3 * n * 4) + align256(n) + align256(np * 4) +
+               B200D_MAX_SRC * align256(np * 4);
+    }
+    Scratch(void *base, int H, int W) {
+        const size_t n = (size_t)H * W, np = (size_t)H * pitch(W);
+        char *p = (char *)(((uintptr_t)base + 255) & ~(uintptr_t)255);
+        auto take = [&](size_t b) { char *q = p; p += align256(b); return q; };
+        mean1 = (float *)take(n * 4);
+        var1 = (float *)take(n * 4);
+        cand = (float *)take(n * 4);
+        best = (float *)take(n * 4);
+        normal_alt = (float *)take(3 * n * 4);
+        valid = (uint8_t *)take(n);
+        rpad = (float *)take(np * 4);
+        smap = (float *)take(np * 4);
+        Wp = pitch(W);
+        map_stride = align256(np * 4) / 4;
+    }
+};
+
+// ---- TMA descriptors (driver entry point resolved at run time: no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tensor_map(CUtensorMap *m, const float *base, int W, int H, size_t pitch_floats, int box_w, int box_h) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) return fail(B200D_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+        fn = (EncodeTiledFn)p;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)H};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch_floats * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed (CUresult %d) W=%d H=%d pitch=%zu box=%dx%d", (int)r, W,
+                 H, pitch_floats, box_w, box_h);
+        return B200D_ERR_CUDA;
+    }
+    return B200D_OK;
+}
+
+// window (TMA box) geometry and column offset of a patch size
+int box_dims(int patch, int *bw, int *bh, int *pad) {
+    switch (patch) {
+        case 3: *bw = Geo<3>::RWP; *bh = Geo<3>::RH; *pad = Geo<3>::PAD; return B200D_OK;
+        case 5: *bw = Geo<5>::RWP; *bh = Geo<5>::RH; *pad = Geo<5>::PAD; return B200D_OK;
+        case 7: *bw = Geo<7>::RWP; *bh = Geo<7>::RH; *pad = Geo<7>::PAD; return B200D_OK;
+        case 9: *bw = Geo<9>::RWP; *bh = Geo<9>::RH; *pad = Geo<9>::PAD; return B200D_OK;
+        case 11: *bw = Geo<11>::RWP; *bh = Geo<11>::RH; *pad = Geo<11>::PAD; return B200D_OK;
+        case 13: *bw = Geo<13>::RWP; *bh = Geo<13>::RH; *pad = Geo<13>::PAD; return B200D_OK;
+        default: return fail(B200D_ERR_ARG, "unsupported patch size (odd 3..13)");
+    }
+}
+
+// Prepare the TMA sources of one view: a column-shifted copy of the reference image, zeroed left
+// margins (the columns that stand for x < 0) and the tensor maps of the reference and of S sampled maps.
+int prepare_tma(int patch, const float *d_ref, int H, int W, int S, const Scratch &sc, NccArgs &n, cudaStream_t st) {
+    int bw, bh, pad;
+    TRY(box_dims(patch, &bw, &bh, &pad));
+    CUDA_TRY(cudaMemcpy2DAsync(sc.rpad + pad, (size_t)sc.Wp * 4, d_ref, (size_t)W * 4, (size_t)W * 4, H,
+                               cudaMemcpyDeviceToDevice, st));
+    if (pad) {
+        CUDA_TRY(cudaMemset2DAsync(sc.rpad, (size_t)sc.Wp * 4, 0, (size_t)pad * 4, H, st));
+        for (int s = 0; s < S; ++s)
+            CUDA_TRY(cudaMemset2DAsync(sc.smap + s * sc.map_stride, (size_t)sc.Wp * 4, 0, (size_t)pad * 4, H, st));
+    }
+    TRY(make_tensor_map(&n.tm_r, sc.rpad, W + pad, H, sc.Wp, bw, bh));
+    for (int s = 0; s < S; ++s) TRY(make_tensor_map(&n.tm_s[s], sc.smap + s * sc.map_stride, W + pad, H, sc.Wp, bw, bh));
+    return B200D_OK;
+}
 
 template <int K, int MODE>
-int launch_pm(const PmArgs &a, cudaStream_t st) {
-    static bool configured = false;          // per instantiation; attribute is idempotent
+int launch_ncc(const NccArgs &a, cudaStream_t st) {
+    static bool configured = false;          // per instantiation; the attribute is idempotent
     if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(pm_eval_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_TRY(cudaFuncSetAttribute(ncc_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)Geo<K>::smem_bytes));
         configured = true;
     }
     ProfScope prof(MODE * 100 + K, st);
-    pm_eval_kernel<K, MODE><<<tile_grid(a.H, a.W), NT, Geo<K>::smem_bytes, st>>>(a);
-    return cuda_check(cudaGetLastError(), "pm_eval_kernel launch");
+    const dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, 1);
+    ncc_kernel<K, MODE><<<grid, NT, Geo<K>::smem_bytes, st>>>(a);
+    return cuda_check(cudaGetLastError(), "ncc_kernel launch");
 }
 
 template <int MODE>
-int launch_pm_k(int patch, const PmArgs &a, cudaStream_t st) {
+int launch_ncc_k(int patch, const NccArgs &a, cudaStream_t st) {
     switch (patch) {
-        case 3: return launch_pm<3, MODE>(a, st);
-        case 5: return launch_pm<5, MODE>(a, st);
-        case 7: return launch_pm<7, MODE>(a, st);
-        case 9: return launch_pm<9, MODE>(a, st);
-        case 11: return launch_pm<11, MODE>(a, st);
-        case 13: return launch_pm<13, MODE>(a, st);
-        default: return fail(B200D_ERR_ARG, "unsupported patch size (odd 3..13)%s");
+        case 3: return launch_ncc<3, MODE>(a, st);
+        case 5: return launch_ncc<5, MODE>(a, st);
+        case 7: return launch_ncc<7, MODE>(a, st);
+        case 9: return launch_ncc<9, MODE>(a, st);
+        case 11: return launch_ncc<11, MODE>(a, st);
+        case 13: return launch_ncc<13, MODE>(a, st);
+        default: return fail(B200D_ERR_ARG, "unsupported patch size (odd 3..13)");
     }
 }
 
-template <int K>
-int launch_sweep(const SweepArgs &a, cudaStream_t st) {
-    constexpr size_t smem = 3 * (size_t)Geo<K>::RH * Geo<K>::RWP * sizeof(float) + (size_t)TH * TW;
-    static bool configured = false;
-    if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(plane_sweep_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    ProfScope prof(1000 + K, st);
-    plane_sweep_kernel<K><<<tile_grid(a.H, a.W), NT, smem, st>>>(a);
-    return cuda_check(cudaGetLastError(), "plane_sweep_kernel launch");
+template <int CAND, int BOUNDS>
+int launch_sample(const SampleArgs &a, cudaStream_t st) {
+    ProfScope prof(2000 + CAND * 10 + BOUNDS, st);
+    const dim3 grid((a.W + SBX - 1) / SBX, (a.H + SBY - 1) / SBY, 1);
+    sample_kernel<CAND, BOUNDS><<<grid, dim3(SBX, SBY, 1), 0, st>>>(a);
+    return cuda_check(cudaGetLastError(), "sample_kernel launch");
 }
 
 int check_common(int H, int W, int patch) {
-    if (H < 2 || W < 2) return fail(B200D_ERR_ARG, "image must be at least 2x2%s");
-    if (patch < 3 || patch > 13 || (patch % 2) == 0) return fail(B200D_ERR_ARG, "unsupported patch size (odd 3..13)%s");
+    if (H < 2 || W < 2) return fail(B200D_ERR_ARG, "image must be at least 2x2");
+    if (patch < 3 || patch > 13 || (patch % 2) == 0) return fail(B200D_ERR_ARG, "unsupported patch size (odd 3..13)");
+    return B200D_OK;
+}
+
+int check_cams(const b200d_cams *cams) {
+    if (!cams) return fail(B200D_ERR_ARG, "null pointer");
+    if (cams->n_src < 1 || cams->n_src > B200D_MAX_SRC) return fail(B200D_ERR_ARG, "n_src out of range");
     return B200D_OK;
 }
 
@@ -123,8 +221,9 @@ __global__ void pm_init_kernel(float *depth, float *normal, float *best, size_t 
         normal[3 * i + 2] = init_normal[3 * i + 2];
     } else {
         // normal = normalize([0.3 randn, 0.3 randn, -1])                     (:275-281)
-        const uint4 r2 = philox4x32_10(make_uint4((uint32_t)i, 0xFFFFFFFFu, view_id, 1u), key);
-        const float a = mul(gauss(r.y, r.z), 0.3f), b = mul(gauss(r2.x, r2.y), 0.3f);
+        float g0, g1;
+        gauss2(r.y, r.z, g0, g1);
+        const float a = mul(g0, 0.3f), b = mul(g1, 0.3f);
         float nn = __fsqrt_rn(add(add(mul(a, a), mul(b, b)), 1.0f));
         nn = nn < 1e-12f ? 1e-12f : nn;
         normal[3 * i] = div_(a, nn);
@@ -134,8 +233,25 @@ __global__ void pm_init_kernel(float *depth, float *normal, float *best, size_t 
     best[i] = __int_as_float(0x7f800000);                                     // +inf (:284)
 }
 
-void fill_srcs(PmArgs &a, const float *const *d_src, int n) {
-    for (int s = 0; s < B200D_MAX_SRC; ++s) a.src[s] = (s < n) ? d_src[s] : nullptr;
+void fill_sample(SampleArgs &s, const float *const *d_src, const b200d_cams *cams, int H, int W, int patch,
+                 const Scratch &sc) {
+    memset(&s, 0, sizeof(s));
+    for (int i = 0; i < cams->n_src; ++i) s.src[i] = d_src[i];
+    s.cams = *cams;
+    s.H = H; s.W = W; s.Wp = sc.Wp; s.map_stride = sc.map_stride;
+    s.half = patch / 2;
+    s.pad = (patch / 2) % 4;
+    s.smap = sc.smap; s.cand = sc.cand; s.valid = sc.valid;
+}
+
+// mean1 / var1: the "sampled image" of the statistics pass is the reference itself.
+int stats_impl(const NccArgs &prepared, int H, int W, int patch, float *mean1, float *var1, cudaStream_t st) {
+    NccArgs n;
+    memset(&n, 0, sizeof(n));
+    n.tm_r = prepared.tm_r;
+    n.tm_s[0] = prepared.tm_r;
+    n.n_src = 1; n.H = H; n.W = W; n.out = mean1; n.out2 = var1;
+    return launch_ncc_k<N_STATS>(patch, n, st);
 }
 
 }  // namespace
@@ -156,7 +272,7 @@ int b200d_device_count(void) {
 
 int b200d_profile_begin(int max_records) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
-    if (max_records < 1 || max_records > (1 << 20)) return fail(B200D_ERR_ARG, "max_records out of range%s");
+    if (max_records < 1 || max_records > (1 << 20)) return fail(B200D_ERR_ARG, "max_records out of range");
     for (auto &r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     g_prof.assign((size_t)max_records, ProfRec{});
     for (auto &r : g_prof) {
@@ -185,164 +301,176 @@ int b200d_profile_end(float *ms_out, int32_t *tag_out, int cap, int *n_out) {
     return rc;
 }
 
-size_t b200d_pm_scratch_bytes(int H, int W) {
-    const size_t n = align256((size_t)H * W * sizeof(float));
-    return 12 * n;          // depth x2, best x2, mean1, var1 (1 plane each) + normal x2 (3 planes each)
+size_t b200d_scratch_bytes(int H, int W) {
+    if (H < 1 || W < 1) return 0;
+    return Scratch::bytes(H, W) + 256;
 }
-
-size_t b200d_sweep_scratch_bytes(int H, int W) { return 2 * (size_t)H * W * sizeof(float); }
 
 size_t b200d_fuse_scratch_bytes(int H, int W) {
     const size_t chunks = ((size_t)H * W + FUSE_CHUNK - 1) / FUSE_CHUNK;
     return align256(chunks * sizeof(uint32_t)) + align256(chunks * sizeof(int64_t));
 }
 
-int b200d_ref_stats(const float *d_ref, int H, int W, int patch, float *d_mean1, float *d_var1, void *stream) {
-    int rc = check_common(H, W, patch);
-    if (rc) return rc;
-    if (!d_ref || !d_mean1 || !d_var1) return fail(B200D_ERR_ARG, "null pointer%s");
-    PmArgs a;
-    memset(&a, 0, sizeof(a));
-    a.ref = d_ref; a.H = H; a.W = W; a.out = d_mean1; a.out2 = d_var1;
-    return launch_pm_k<M_STATS>(patch, a, (cudaStream_t)stream);
+int b200d_ref_stats(const float *d_ref, int H, int W, int patch, float *d_mean1, float *d_var1, void *d_scratch,
+                    void *stream) {
+    TRY(check_common(H, W, patch));
+    if (!d_ref || !d_mean1 || !d_var1 || !d_scratch) return fail(B200D_ERR_ARG, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    Scratch sc(d_scratch, H, W);
+    NccArgs n;
+    memset(&n, 0, sizeof(n));
+    TRY(prepare_tma(patch, d_ref, H, W, 0, sc, n, st));
+    return stats_impl(n, H, W, patch, d_mean1, d_var1, st);
 }
 
-int b200d_pm_cost(const float *d_ref, const float *d_mean1, const float *d_var1, const float *const *d_src,
-                  const b200d_cams *cams, const float *d_depth, int H, int W, int patch, int mode, int arith,
-                  float *d_out, void *stream) {
-    int rc = check_common(H, W, patch);
-    if (rc) return rc;
-    if (!d_ref || !d_mean1 || !d_var1 || !d_src || !cams || !d_depth || !d_out) return fail(B200D_ERR_ARG, "null pointer%s");
-    if (cams->n_src < 1 || cams->n_src > B200D_MAX_SRC) return fail(B200D_ERR_ARG, "n_src out of range%s");
-    if (arith != B200D_PARITY) return fail(B200D_ERR_UNSUPPORTED, "fast arithmetic not built yet%s");
-    PmArgs a;
-    memset(&a, 0, sizeof(a));
-    a.ref = d_ref; a.mean1 = d_mean1; a.var1 = d_var1; a.cams = *cams; a.H = H; a.W = W;
-    fill_srcs(a, d_src, cams->n_src);
-    a.depth_in = d_depth; a.out = d_out;
-    if (mode == 0) return launch_pm_k<M_COST>(patch, a, (cudaStream_t)stream);
-    if (mode == 1) return launch_pm_k<M_CONF>(patch, a, (cudaStream_t)stream);
-    return fail(B200D_ERR_ARG, "mode must be 0 (cost) or 1 (confidence)%s");
+int b200d_pm_cost(const float *d_ref, const float *const *d_src, const b200d_cams *cams, const float *d_depth, int H,
+                  int W, int patch, int mode, int arith, float *d_out, void *d_scratch, void *stream) {
+    TRY(check_common(H, W, patch));
+    TRY(check_cams(cams));
+    if (!d_ref || !d_src || !d_depth || !d_out || !d_scratch) return fail(B200D_ERR_ARG, "null pointer");
+    if (mode != 0 && mode != 1) return fail(B200D_ERR_ARG, "mode must be 0 (cost) or 1 (confidence)");
+    if (arith != B200D_PARITY) return fail(B200D_ERR_UNSUPPORTED, "fast arithmetic not built yet");
+    cudaStream_t st = (cudaStream_t)stream;
+    Scratch sc(d_scratch, H, W);
+    NccArgs n;
+    memset(&n, 0, sizeof(n));
+    TRY(prepare_tma(patch, d_ref, H, W, cams->n_src, sc, n, st));
+    TRY(stats_impl(n, H, W, patch, sc.mean1, sc.var1, st));
+    SampleArgs s;
+    fill_sample(s, d_src, cams, H, W, patch, sc);
+    s.depth_in = d_depth;
+    n.n_src = cams->n_src; n.H = H; n.W = W; n.mean1 = sc.mean1; n.var1 = sc.var1; n.valid = sc.valid; n.cand = sc.cand;
+    n.out = d_out;
+    if (mode == 0) {
+        TRY((launch_sample<C_MAP, B_PATCH>(s, st)));
+        return launch_ncc_k<N_COST>(patch, n, st);
+    }
+    TRY((launch_sample<C_MAP, B_IMAGE>(s, st)));
+    return launch_ncc_k<N_CONF>(patch, n, st);
 }
 
 int b200d_pm_view(const float *d_ref, const float *const *d_src, const b200d_cams *cams, int H, int W,
                   const b200d_pm_params *prm, const b200d_rng *rng, void *d_scratch, float *d_depth, float *d_normal,
                   float *d_conf, float *d_best, float *d_costs, void *stream) {
-    if (!prm) return fail(B200D_ERR_ARG, "null params%s");
-    int rc = check_common(H, W, prm->patch);
-    if (rc) return rc;
-    if (!d_ref || !d_src || !cams || !rng || !d_scratch || !d_depth || !d_normal || !d_conf)
-        return fail(B200D_ERR_ARG, "null pointer%s");
-    if (cams->n_src < 1 || cams->n_src > B200D_MAX_SRC) return fail(B200D_ERR_ARG, "n_src out of range%s");
-    if (prm->iters < 0 || prm->samples < 0) return fail(B200D_ERR_ARG, "negative iteration count%s");
-    if (prm->arith != B200D_PARITY) return fail(B200D_ERR_UNSUPPORTED, "fast arithmetic not built yet%s");
+    if (!prm) return fail(B200D_ERR_ARG, "null params");
+    TRY(check_common(H, W, prm->patch));
+    TRY(check_cams(cams));
+    if (!d_ref || !d_src || !rng || !d_scratch || !d_depth || !d_normal || !d_conf) return fail(B200D_ERR_ARG, "null pointer");
+    if (prm->iters < 0 || prm->samples < 0) return fail(B200D_ERR_ARG, "negative iteration count");
+    if (prm->arith != B200D_PARITY) return fail(B200D_ERR_UNSUPPORTED, "fast arithmetic not built yet");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)H * W;
-    const size_t plane = align256(n * sizeof(float));
-    char *base = (char *)d_scratch;
-    float *depth[2] = {(float *)(base), (float *)(base + plane)};
-    float *best[2] = {(float *)(base + 2 * plane), (float *)(base + 3 * plane)};
-    float *mean1 = (float *)(base + 4 * plane), *var1 = (float *)(base + 5 * plane);
-    float *normal[2] = {(float *)(base + 6 * plane), (float *)(base + 9 * plane)};
+    const int patch = prm->patch;
+    Scratch sc(d_scratch, H, W);
+    // State lives in the caller's output buffers: depth and best are updated in place (only winners
+    // write).  Normals ping-pong across the two shifted evaluations of an iteration because a shift
+    // reads the neighbour's normal; two flips per iteration -> the result always ends in d_normal.
+    float *depth = d_depth, *best = d_best ? d_best : sc.best;
+    float *normal[2] = {d_normal, sc.normal_alt};
 
-    rc = b200d_ref_stats(d_ref, H, W, prm->patch, mean1, var1, stream);
-    if (rc) return rc;
+    NccArgs a;
+    memset(&a, 0, sizeof(a));
+    TRY(prepare_tma(patch, d_ref, H, W, cams->n_src, sc, a, st));
+    TRY(stats_impl(a, H, W, patch, sc.mean1, sc.var1, st));
 
     const double ld0 = log(prm->depth_min), ld1 = log(prm->depth_max);
-    pm_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(depth[0], normal[0], best[0], n, (float)(ld1 - ld0),
-                                                                (float)ld0, rng->d_init_depth, rng->d_init_normal,
-                                                                rng->seed, rng->view_id);
+    {
+        ProfScope prof(3000, st);
+        pm_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(depth, normal[0], best, n, (float)(ld1 - ld0), (float)ld0,
+                                                                    rng->d_init_depth, rng->d_init_normal, rng->seed,
+                                                                    rng->view_id);
+    }
     CUDA_TRY(cudaGetLastError());
 
-    PmArgs a;
-    memset(&a, 0, sizeof(a));
-    a.ref = d_ref; a.mean1 = mean1; a.var1 = var1; a.cams = *cams; a.H = H; a.W = W;
-    fill_srcs(a, d_src, cams->n_src);
-    a.depth_min = (float)prm->depth_min;
-    a.depth_max = (float)prm->depth_max;
+    SampleArgs s;
+    fill_sample(s, d_src, cams, H, W, patch, sc);
+    s.depth_in = depth;
+    s.depth_min = (float)prm->depth_min;
+    s.depth_max = (float)prm->depth_max;
+    s.seed = rng->seed;
+    s.view_id = rng->view_id;
+
+    a.n_src = cams->n_src; a.H = H; a.W = W; a.mean1 = sc.mean1; a.var1 = sc.var1; a.valid = sc.valid; a.cand = sc.cand;
+    a.depth_in = a.depth_out = depth;
+    a.best_in = a.best_out = best;
     a.seed = rng->seed;
     a.view_id = rng->view_id;
 
-    int cd = 0, cn = 0, cb = 0, e = 0;
+    int cn = 0, e = 0;
     for (int it = 0; it < prm->iters; ++it) {
         const int sgn = (it % 2 == 0) ? 1 : -1;       // slicing semantics of :429-442
         for (int o = 0; o < 2; ++o) {
-            a.dy = (o == 0) ? sgn : 0;
-            a.dx = (o == 0) ? 0 : sgn;
-            a.depth_in = depth[cd]; a.normal_in = normal[cn]; a.best_in = best[cb];
-            a.depth_out = depth[cd ^ 1]; a.normal_out = normal[cn ^ 1]; a.best_out = best[cb ^ 1];
+            s.dy = a.dy = (o == 0) ? sgn : 0;
+            s.dx = a.dx = (o == 0) ? 0 : sgn;
+            s.eval_id = a.eval_id = (uint32_t)e;
+            TRY((launch_sample<C_SHIFT, B_PATCH>(s, st)));
+            a.normal_in = normal[cn]; a.normal_out = normal[cn ^ 1];
             a.out = d_costs ? d_costs + (size_t)e * n : nullptr;
-            a.eval_id = (uint32_t)e;
-            rc = launch_pm_k<M_SHIFT>(prm->patch, a, st);
-            if (rc) return rc;
-            cd ^= 1; cn ^= 1; cb ^= 1; ++e;
+            TRY(launch_ncc_k<N_SHIFT>(patch, a, st));
+            cn ^= 1; ++e;
         }
-        a.dr = (float)((prm->depth_max - prm->depth_min) * pow(0.5, it));      // :466
+        s.dr = (float)((prm->depth_max - prm->depth_min) * pow(0.5, it));      // :466
         a.nr = (float)(0.5 * pow(0.5, it));                                    // :467
         for (int sm = 0; sm < prm->samples; ++sm) {
             const size_t k = (size_t)it * prm->samples + sm;
-            a.rand_u = rng->d_rand_u ? rng->d_rand_u + k * n : nullptr;
+            s.rand_u = rng->d_rand_u ? rng->d_rand_u + k * n : nullptr;
             a.rand_n = rng->d_rand_n ? rng->d_rand_n + k * n * 3 : nullptr;
-            a.depth_in = depth[cd]; a.depth_out = depth[cd ^ 1];
+            s.eval_id = a.eval_id = (uint32_t)e;
+            TRY((launch_sample<C_REFINE, B_PATCH>(s, st)));
             a.normal_in = a.normal_out = normal[cn];                            // pixel-local: in place
-            a.best_in = a.best_out = best[cb];
             a.out = d_costs ? d_costs + (size_t)e * n : nullptr;
-            a.eval_id = (uint32_t)e;
-            rc = launch_pm_k<M_REFINE>(prm->patch, a, st);
-            if (rc) return rc;
-            cd ^= 1; ++e;
+            TRY(launch_ncc_k<N_REFINE>(patch, a, st));
+            ++e;
         }
     }
-    a.depth_in = depth[cd];
+    if (cn != 0) CUDA_TRY(cudaMemcpyAsync(d_normal, normal[cn], 3 * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    TRY((launch_sample<C_MAP, B_IMAGE>(s, st)));
     a.out = d_conf;
-    rc = launch_pm_k<M_CONF>(prm->patch, a, st);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(d_depth, depth[cd], n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(d_normal, normal[cn], 3 * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    if (d_best) CUDA_TRY(cudaMemcpyAsync(d_best, best[cb], n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    return B200D_OK;
+    return launch_ncc_k<N_CONF>(patch, a, st);
 }
 
-int b200d_plane_sweep(const float *d_ref, const float *const *d_nbr, const b200d_cams *cams, const float *d_depths,
+int b200d_plane_sweep(const float *d_ref, const float *const *d_nbr, const b200d_cams *cams, const float *depths_host,
                       int D, int H, int W, int patch, float thresh, int arith, float *d_depth_map, float *d_conf,
                       int32_t *d_idx, float *d_ncc, void *d_scratch, void *stream) {
-    int rc = check_common(H, W, patch);
-    if (rc) return rc;
-    if (!d_ref || !d_nbr || !cams || !d_depths || !d_depth_map || !d_conf || !d_idx || !d_scratch) return fail(B200D_ERR_ARG, "null pointer%s");
-    if (D < 1) return fail(B200D_ERR_ARG, "need at least one depth plane%s");
-    if (cams->n_src < 1 || cams->n_src > B200D_MAX_SRC) return fail(B200D_ERR_ARG, "n_src out of range%s");
-    if (arith != B200D_PARITY) return fail(B200D_ERR_UNSUPPORTED, "fast arithmetic not built yet%s");
-    const size_t n = (size_t)H * W;
-    float *stats = (float *)d_scratch;               // mean1 | var1 of the reference view
-    rc = b200d_ref_stats(d_ref, H, W, patch, stats, stats + n, stream);
-    if (rc == B200D_OK) {
-        SweepArgs a;
-        memset(&a, 0, sizeof(a));
-        a.ref = d_ref; a.mean1 = stats; a.var1 = stats + n; a.cams = *cams; a.H = H; a.W = W; a.D = D;
-        for (int s = 0; s < B200D_MAX_SRC; ++s) a.nbr[s] = (s < cams->n_src) ? d_nbr[s] : nullptr;
-        a.depths = d_depths; a.thresh = thresh;
-        a.depth_map = d_depth_map; a.conf = d_conf; a.idx = d_idx; a.ncc = d_ncc;
-        cudaStream_t st = (cudaStream_t)stream;
-        switch (patch) {
-            case 3: rc = launch_sweep<3>(a, st); break;
-            case 5: rc = launch_sweep<5>(a, st); break;
-            case 7: rc = launch_sweep<7>(a, st); break;
-            case 9: rc = launch_sweep<9>(a, st); break;
-            case 11: rc = launch_sweep<11>(a, st); break;
-            case 13: rc = launch_sweep<13>(a, st); break;
-            default: rc = fail(B200D_ERR_ARG, "unsupported patch size (odd 3..13)%s");
-        }
+    TRY(check_common(H, W, patch));
+    TRY(check_cams(cams));
+    if (!d_ref || !d_nbr || !depths_host || !d_depth_map || !d_conf || !d_idx || !d_scratch)
+        return fail(B200D_ERR_ARG, "null pointer");
+    if (D < 1) return fail(B200D_ERR_ARG, "need at least one depth plane");
+    if ((size_t)D > (size_t)H * W) return fail(B200D_ERR_ARG, "more planes than pixels");
+    if (arith != B200D_PARITY) return fail(B200D_ERR_UNSUPPORTED, "fast arithmetic not built yet");
+    cudaStream_t st = (cudaStream_t)stream;
+    Scratch sc(d_scratch, H, W);
+    NccArgs a;
+    memset(&a, 0, sizeof(a));
+    TRY(prepare_tma(patch, d_ref, H, W, cams->n_src, sc, a, st));
+    TRY(stats_impl(a, H, W, patch, sc.mean1, sc.var1, st));
+    // plane depths: kernel argument per plane (host) and a device copy for the final gather; the
+    // candidate map of the scratch is unused by the sweep and holds the D floats
+    float *d_depths = sc.cand;
+    CUDA_TRY(cudaMemcpyAsync(d_depths, depths_host, (size_t)D * sizeof(float), cudaMemcpyHostToDevice, st));
+    SampleArgs s;
+    fill_sample(s, d_nbr, cams, H, W, patch, sc);
+    s.cand = nullptr;
+    a.n_src = cams->n_src; a.H = H; a.W = W; a.mean1 = sc.mean1; a.var1 = sc.var1; a.valid = sc.valid;
+    a.thresh = thresh; a.n_planes = D; a.depths = d_depths;
+    a.conf = d_conf; a.idx = d_idx; a.depth_map = d_depth_map; a.ncc = d_ncc;
+    for (int d = 0; d < D; ++d) {
+        s.plane_depth = depths_host[d];
+        a.plane = d;
+        TRY((launch_sample<C_PLANE, B_DEPTH>(s, st)));
+        TRY(launch_ncc_k<N_SWEEP>(patch, a, st));
     }
-    return rc;
+    return B200D_OK;
 }
 
 int b200d_mask_backproject(const float *d_depth, const float *d_conf, const uint8_t *d_bgr, int H, int W,
                            const double *Kinv64, const double *R64, const double *t64, float min_conf, int mode,
                            double *d_points, uint8_t *d_colors, int64_t *d_count, void *d_scratch, void *stream) {
-    if (H < 1 || W < 1) return fail(B200D_ERR_ARG, "empty image%s");
+    if (H < 1 || W < 1) return fail(B200D_ERR_ARG, "empty image");
     if (!d_depth || !d_conf || !d_bgr || !Kinv64 || !R64 || !t64 || !d_points || !d_colors || !d_count || !d_scratch)
-        return fail(B200D_ERR_ARG, "null pointer%s");
-    if (mode != 0 && mode != 1) return fail(B200D_ERR_ARG, "mode must be 0 (PatchMatch) or 1 (plane sweep)%s");
+        return fail(B200D_ERR_ARG, "null pointer");
+    if (mode != 0 && mode != 1) return fail(B200D_ERR_ARG, "mode must be 0 (PatchMatch) or 1 (plane sweep)");
     FuseArgs a;
     memset(&a, 0, sizeof(a));
     a.depth = d_depth; a.conf = d_conf; a.bgr = d_bgr; a.H = H; a.W = W; a.min_conf = min_conf; a.mode = mode;
@@ -355,6 +483,7 @@ int b200d_mask_backproject(const float *d_depth, const float *d_conf, const uint
     a.chunk_counts = (uint32_t *)d_scratch;
     a.chunk_offsets = (int64_t *)((char *)d_scratch + align256(chunks * sizeof(uint32_t)));
     cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(4000, st);
     fuse_count_kernel<<<(unsigned)chunks, FUSE_NT, 0, st>>>(a);
     fuse_scan_kernel<<<1, 1024, 0, st>>>(a);
     fuse_write_kernel<<<(unsigned)chunks, FUSE_NT, 0, st>>>(a);

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(HERE, 'libb200dense.so')
 SRCS = ['b200dense.cu']
-DEPS = SRCS + ['device_math.cuh', 'pm_kernels.cuh', 'sweep_kernels.cuh', 'fuse_kernels.cuh',
+DEPS = SRCS + ['device_math.cuh', 'sample_kernels.cuh', 'ncc_kernels.cuh', 'fuse_kernels.cuh',
                os.path.join(ROOT, 'include', 'b200dense.h')]
 
 
@@ -32,16 +32,21 @@ def stale():
     return any(os.path.getmtime(os.path.join(HERE, d)) > t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, out=None, defines=()):
+    """Default build -> csrc/libb200dense.so.  `out` + `defines` build a tuning variant elsewhere."""
+    if out is None and not force and not stale():
         return OUT
-    cmd = [nvcc(), '-shared', '-Xcompiler', '-fPIC,-fvisibility=hidden', '-std=c++17', '-O3', '-lineinfo',
+    if out is not None:
+        OUT_ = out
+    else:
+        OUT_ = OUT
+    cmd = [nvcc(), *[f'-D{d}' for d in defines], '-shared', '-Xcompiler', '-fPIC,-fvisibility=hidden', '-std=c++17', '-O3', '-lineinfo',
            '-gencode', 'arch=compute_100a,code=sm_100a', '-fmad=false', '-ccbin', '/usr/bin/g++',
-           '-I', os.path.join(ROOT, 'include'), '-I', HERE, '-o', OUT] + [os.path.join(HERE, s) for s in SRCS]
+           '-I', os.path.join(ROOT, 'include'), '-I', HERE, '-o', OUT_] + [os.path.join(HERE, s) for s in SRCS]
     if verbose:
         cmd.insert(1, '-Xptxas=-v')
     subprocess.check_call(cmd)
-    return OUT
+    return OUT_
 
 
 if __name__ == '__main__':

@@ -155,7 +155,7 @@ class DenseStereoReconstructor:
         eng = self.engine
         cams = make_cams(self.K_scaled, kinv32(self.K_scaled), poses[ref_idx].R, poses[ref_idx].t,
                          [poses[i].R for i in neighbor_indices], [poses[i].t for i in neighbor_indices])
-        depths = eng.to_device(self._plane_depths(depth_min, depth_max).astype(np.float32))
+        depths = self._plane_depths(depth_min, depth_max).astype(np.float32)
         return eng.plane_sweep(self._gray_on_device(processed, ref_idx),
                                [self._gray_on_device(processed, i) for i in neighbor_indices], cams, depths,
                                self.patch_size, self.consistency_thresh)

@@ -89,9 +89,11 @@ typedef struct {
     double depth_min, depth_max;
 } b200d_pm_params;
 
-/* Scratch for one PatchMatch view: ping-pong state + reference window statistics.
- * b200d_pm_scratch_bytes(H,W) bytes of device memory, 256-byte aligned. */
-B200D_API size_t b200d_pm_scratch_bytes(int H, int W);
+/* Device scratch of one view in flight, shared by all compute entry points below:
+ * reference window statistics, candidate depth, validity bits, a pitch-padded copy of the reference
+ * (TMA source when W is not a multiple of 4) and B200D_MAX_SRC pitch-padded sampled images
+ * (~81 bytes per pixel).  Calls that may run concurrently (different streams) need different scratch. */
+B200D_API size_t b200d_scratch_bytes(int H, int W);
 
 B200D_API int b200d_abi_version(void);
 B200D_API const char *b200d_last_error(void);
@@ -100,19 +102,21 @@ B200D_API int b200d_device_count(void);
 /* Reference-side window statistics mean1 = box(r), var1 = box(r*r) - mean1^2
  * (first two conv2d of _ncc_cost / _compute_ncc_torch, mvs_patchmatch.py:403-406,
  * dense_stereo.py:333-337; constant per reference view). */
-B200D_API int b200d_ref_stats(const float *d_ref, int H, int W, int patch, float *d_mean1, float *d_var1, void *stream);
+B200D_API int b200d_ref_stats(const float *d_ref, int H, int W, int patch, float *d_mean1, float *d_var1,
+                              void *d_scratch, void *stream);
 
 /* Replaces PatchMatchMVS._compute_patch_cost (mvs_patchmatch.py:323-390) when mode==0 and
  * PatchMatchMVS._compute_confidence (:493-534) when mode==1, for a given per-pixel depth map.
- * d_src[s] are the source grays (H,W) fp32.  d_mean1/d_var1 from b200d_ref_stats. */
-B200D_API int b200d_pm_cost(const float *d_ref, const float *d_mean1, const float *d_var1,
-                  const float *const *d_src, const b200d_cams *cams, const float *d_depth,
-                  int H, int W, int patch, int mode, int arith, float *d_out, void *stream);
+ * d_src[s] are the source grays (H,W) fp32; d_out (H,W) receives the cost (may hold +inf / NaN) or the
+ * count of consistent sources. */
+B200D_API int b200d_pm_cost(const float *d_ref, const float *const *d_src, const b200d_cams *cams,
+                            const float *d_depth, int H, int W, int patch, int mode, int arith, float *d_out,
+                            void *d_scratch, void *stream);
 
 /* Replaces PatchMatchMVS._patchmatch_cuda (mvs_patchmatch.py:225-321) from initialisation to the
  * confidence map: init -> iters x (2 shifted-neighbour evaluations + `samples` random
  * refinements, strict `<` selection) -> confidence.  Results: d_depth (H,W), d_normal (H,W,3),
- * d_conf (H,W), optional d_best (H,W).  d_costs (iters*(2+samples),H,W) optional dump of every
+ * d_conf (H,W), optional d_best (H,W); d_scratch: b200d_scratch_bytes(H,W) bytes.  d_costs (iters*(2+samples),H,W) optional dump of every
  * evaluated cost map (tests). */
 B200D_API int b200d_pm_view(const float *d_ref, const float *const *d_src, const b200d_cams *cams,
                   int H, int W, const b200d_pm_params *prm, const b200d_rng *rng,
@@ -122,14 +126,13 @@ B200D_API int b200d_pm_view(const float *d_ref, const float *const *d_src, const
 /* Replaces DenseStereoReconstructor._plane_sweep_torch (dense_stereo.py:222-316):
  * for each plane d (given order) and neighbour n: reproject at constant depth, bilinear sample,
  * box NCC (_compute_ncc_torch :318-347), count (ncc > thresh) & (z > 0.1); first arg-max over d.
- * d_depths (D) fp32.  Outputs d_depth_map, d_conf (H,W) fp32, d_idx (H,W) int32;
- * d_ncc (D,N,H,W) optional dump of the NCC volume (tests).
- * d_scratch: b200d_sweep_scratch_bytes(H,W) bytes (reference window statistics). */
-B200D_API size_t b200d_sweep_scratch_bytes(int H, int W);
+ * depths (D) fp32 in HOST memory (each plane is a kernel argument).  Outputs d_depth_map, d_conf (H,W)
+ * fp32, d_idx (H,W) int32; d_ncc (D,N,H,W) optional dump of the NCC volume (tests).
+ * d_scratch: b200d_scratch_bytes(H,W) bytes. */
 B200D_API int b200d_plane_sweep(const float *d_ref, const float *const *d_nbr, const b200d_cams *cams,
-                      const float *d_depths, int D, int H, int W, int patch, float thresh, int arith,
-                      float *d_depth_map, float *d_conf, int32_t *d_idx, float *d_ncc, void *d_scratch,
-                      void *stream);
+                                const float *depths, int D, int H, int W, int patch, float thresh, int arith,
+                                float *d_depth_map, float *d_conf, int32_t *d_idx, float *d_ncc, void *d_scratch,
+                                void *stream);
 
 /* Replaces the per-view body of PatchMatchMVS._fuse_depth_maps (mvs_patchmatch.py:545-565, mode 0:
  * valid = conf >= min_conf) and DenseStereoReconstructor._backproject (dense_stereo.py:414-437,
@@ -146,8 +149,8 @@ B200D_API int b200d_mask_backproject(const float *d_depth, const float *d_conf, 
 /* Optional per-launch timing for benchmarks.  Between _begin and _end every tile kernel launched by
  * this library is bracketed by CUDA events on its own stream (library-owned events, at most
  * max_records launches).  _end waits for the recorded launches, writes their durations (ms) and tags
- * (PatchMatch kernels: mode*100 + patch with mode 0 stats, 1 cost, 2 confidence, 3 shift, 4 refine;
- * plane sweep: 1000 + patch) and releases the events.  Not meant to be left on in production. */
+ * (NCC kernels: mode*100 + patch with mode 0 stats, 1 cost, 2 confidence, 3 shift, 4 refine, 5 plane
+ * sweep; sampling kernels: 2000 + 10*candidate + bounds; init 3000; fusion 4000) and releases the events.  Not meant to be left on in production. */
 B200D_API int b200d_profile_begin(int max_records);
 B200D_API int b200d_profile_end(float *ms_out, int32_t *tag_out, int cap, int *n_out);
 

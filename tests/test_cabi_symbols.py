@@ -37,16 +37,16 @@ def test_abi_version_and_struct_layout():
     # b200d_cams: 9+9+9+3 floats, int32, 8*9 + 8*3 floats
     assert C.sizeof(_cabi.Cams) == 4 * (30 + 1 + 72 + 24)
     assert C.sizeof(_cabi.PmParams) == 4 * 4 + 2 * 8
-    assert lib.b200d_pm_scratch_bytes(1200, 1600) >= 12 * 1200 * 1600 * 4
-    assert lib.b200d_sweep_scratch_bytes(10, 10) == 800
+    assert lib.b200d_scratch_bytes(1200, 1600) >= 16 * 1200 * 1600 * 4
+    assert lib.b200d_scratch_bytes(0, 10) == 0
     assert lib.b200d_fuse_scratch_bytes(10, 10) > 0
 
 
 def test_argument_errors_do_not_touch_cuda():
     lib = _cabi.load()
-    rc = lib.b200d_ref_stats(None, 10, 10, 4, None, None, None)     # even patch
+    rc = lib.b200d_ref_stats(None, 10, 10, 4, None, None, None, None)     # even patch
     assert rc == -1 and b'patch' in lib.b200d_last_error()
-    rc = lib.b200d_ref_stats(None, 10, 10, 5, None, None, None)     # null pointers
+    rc = lib.b200d_ref_stats(None, 10, 10, 5, None, None, None, None)     # null pointers
     assert rc == -1 and b'null' in lib.b200d_last_error()
     with pytest.raises(_cabi.B200DenseError):
         _cabi.check(rc)

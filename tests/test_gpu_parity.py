@@ -40,7 +40,7 @@ def test_plane_sweep_vs_reference_and_oracle(engine, name):
     k, th = int(g['patch']), float(g['thresh'])
     d32 = g['depths'].astype(np.float32)
     r = engine.plane_sweep(dev(engine, g['gray'][ref]), [dev(engine, g['gray'][i]) for i in nb],
-                           engine_cams(g, ref, nb), dev(engine, d32), k, th, dump_ncc=True)
+                           engine_cams(g, ref, nb), d32, k, th, dump_ncc=True)
     depth_map, conf = r['depth_map'].cpu().numpy(), r['confidence'].cpu().numpy()
     idx, ncc = r['best_idx'].cpu().numpy(), r['ncc'].cpu().numpy()
     # vs reference fixture
