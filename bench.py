@@ -237,7 +237,6 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    eng.profile_begin(65536)
     l0 = eng.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     barrier()
@@ -249,7 +248,6 @@ def main():
     barrier()
     ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
     launches = eng.launches - l0
-    kms, ktag = eng.profile_end()
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -257,11 +255,24 @@ def main():
     ms = float(t.item())
     value = V * world * a.steps / (ms / 1e3)
 
-    # ---- dominant kernel: refine evaluation (tag 4*100 + patch); algorithmic bytes per launch
-    dom = kms[ktag == 400 + a.patch]
-    all_pm = kms[(ktag // 100 >= 0) & (ktag < 1000)]
-    dom_ms = float(dom.mean()) if len(dom) else float('nan')
-    alg_bytes = (44 + 4 * a.src) * H * W                      # images 4(1+S) + state 2*(4+12+4)
+    # ---- per-kernel durations: one more step right after the timed region, views serialised on one stream
+    # (with several views in flight the kernels of different views overlap and a per-launch time is not
+    # attributable), CUDA events on the launching stream around every launch (b200d_profile_begin/_end).
+    flush.zero_()
+    eng.profile_begin(65536)
+    eng.run_views(jobs, 1)
+    torch.cuda.synchronize()
+    kms, ktag = eng.profile_end()
+    names = {400 + a.patch: 'ncc_kernel<REFINE>', 300 + a.patch: 'ncc_kernel<SHIFT>', 200 + a.patch: 'ncc_kernel<CONF>',
+             a.patch: 'ncc_kernel<STATS>', 2020: 'sample_kernel<REFINE>', 2010: 'sample_kernel<SHIFT>',
+             2001: 'sample_kernel<MAP,conf>', 3000: 'pm_init_kernel', 4000: 'fuse kernels (3)'}
+    tot_k = float(kms.sum())
+    kernels = {names.get(int(tg), str(int(tg))): {'launches_per_step': int((ktag == tg).sum()),
+                                                   'avg_ms': float(kms[ktag == tg].mean()),
+                                                   'share_of_step': float(kms[ktag == tg].sum() / tot_k)}
+               for tg in np.unique(ktag)}
+    dom_ms = kernels['ncc_kernel<REFINE>']['avg_ms']
+    smp_ms = kernels['sample_kernel<REFINE>']['avg_ms']
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -269,23 +280,34 @@ def main():
         pass
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
     peak_src = 'MEASURED_PEAKS.json hbm_gbs (of measured)' if 'hbm_gbs' in peaks else '6650 GB/s (of fallback)'
+    # algorithmic HBM bytes of one cost evaluation = images 4(1+S) + state 2*(4+12+4) per pixel.
+    # One evaluation = sample_kernel + ncc_kernel; the sampled images in between are L2-resident scratch.
+    alg_bytes = (44 + 4 * a.src) * H * W
     ach = alg_bytes / (dom_ms * 1e-3) / 1e9
-    sm_mhz = (clocks or {}).get('sm_mhz') or peaks.get('sm_max_mhz', 1965.0)
-    evals = H * W * a.src                                     # pixel x source evaluations per launch
+    evals = H * W * a.src                                     # (pixel, source) evaluations per launch
+    fma_peak_nominal = 148 * 128 * peaks.get('sm_max_mhz', 1965.0) * 1e6 / 1e12
+    FMA_PEAK_MEASURED = 36.3                                  # T lane-FMA/s, profiles/microbench/ffma2.cu on B200
+    pair_s = (dom_ms + smp_ms) * 1e-3
     fp32 = {
-        'note': 'binding resource is the FP32 pipe, not HBM (SURVEY 8d); lane-ops count an FMA as one',
-        'eval_sources_per_s': evals / (dom_ms * 1e-3),
-        'peak_tlaneops_at_max_clock': 148 * 128 * peaks.get('sm_max_mhz', 1965.0) * 1e6 / 1e12,
-        'peak_tlaneops_at_measured_clock': 148 * 128 * sm_mhz * 1e6 / 1e12,
-        'achieved_tlaneops_fast_model': evals * (40 + 6 * (a.patch - 1)) / (dom_ms * 1e-3) / 1e12,
-        'achieved_tlaneops_parity_model': evals * (40 + 3 * a.patch * a.patch) / (dom_ms * 1e-3) / 1e12,
+        'note': 'the evaluation is FP32-pipe bound, not HBM bound (SURVEY 8d); lane-ops count an FMA as one; '
+                'parity arithmetic needs 3k^2 FMAs per (pixel, source) by construction',
+        'eval_sources_per_s_ncc_kernel': evals / (dom_ms * 1e-3),
+        'eval_sources_per_s_sample_plus_ncc': evals / pair_s,
+        'peak_tlaneops_nominal': fma_peak_nominal, 'peak_tlaneops_measured_ffma': FMA_PEAK_MEASURED,
+        'ncc_kernel_fma_tlaneops': evals * (3 * a.patch * a.patch + 2 * (a.patch + 3) * 14 / 8 + 20) / (dom_ms * 1e-3) / 1e12,
+        'pair_tlaneops_parity_model': evals * (40 + 3 * a.patch * a.patch) / pair_s / 1e12,
+        'pair_tlaneops_fast_model': evals * (40 + 6 * (a.patch - 1)) / pair_s / 1e12,
     }
-    fp32['frac_fast_model'] = fp32['achieved_tlaneops_fast_model'] / fp32['peak_tlaneops_at_max_clock']
-    fp32['frac_parity_model'] = fp32['achieved_tlaneops_parity_model'] / fp32['peak_tlaneops_at_max_clock']
+    fp32['ncc_kernel_frac_of_measured_fma_peak'] = fp32['ncc_kernel_fma_tlaneops'] / FMA_PEAK_MEASURED
+    fp32['pair_frac_parity_model'] = fp32['pair_tlaneops_parity_model'] / FMA_PEAK_MEASURED
+    fp32['pair_frac_fast_model'] = fp32['pair_tlaneops_fast_model'] / FMA_PEAK_MEASURED
     roofline = {'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
-                'traffic': None, 'kernel': f'pm_eval_kernel<{a.patch},REFINE>', 'launch_ms': dom_ms,
-                'launches_timed': int(len(dom)), 'kernel_share_of_step': float(dom.sum() / max(all_pm.sum(), 1e-9)),
-                'algorithmic_bytes_per_launch': alg_bytes, 'peak_source': peak_src, 'fp32': fp32}
+                'traffic': None, 'kernel': f'ncc_kernel<{a.patch},REFINE>', 'launch_ms': dom_ms,
+                'launches_timed': kernels['ncc_kernel<REFINE>']['launches_per_step'],
+                'kernel_share_of_step': kernels['ncc_kernel<REFINE>']['share_of_step'],
+                'algorithmic_bytes_per_launch': alg_bytes, 'peak_source': peak_src,
+                'how': 'CUDA events on the launching stream around every launch, one serialised step right after the '
+                       'timed region', 'kernels': kernels, 'fp32': fp32}
 
     # ---- end to end through the reference-facing API with pinned host buffers
     e2e = None
