@@ -1,0 +1,132 @@
+"""View-sharded multi-GPU plumbing (one process per GPU, torch.distributed; NCCL on GPUs, gloo in CPU tests).
+
+The reference is single-process (no distributed code).  Its dense stage treats every
+reference view independently, so the path shards by views with no data-path collective:
+
+    rank r computes views[r::world]        (round-robin keeps turntable neighbours on different GPUs)
+
+Only two exchanges exist:
+  * `gather_point_clouds` -- the fused points/colours of all views are collected on rank 0 in sorted
+    view order, which is the order the reference's `np.vstack` over its depth-map dict produces
+    (mvs_patchmatch.py:544-570, dense_stereo.py:138-139).  Variable-length: one all-gather of the
+    per-view counts, then one point-to-point transfer per rank.
+  * `all_gather_maps` -- depth (+normal) maps of all views on every rank, needed only by the opt-in
+    geometric consistency filter (an extension: the reference's own check is photometric).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_views(views: Sequence[int], rank: int = None, world_size: int = None) -> List[int]:
+    """Views owned by `rank`: views[rank::world]."""
+    if rank is None or world_size is None:
+        rank, world_size = world()
+    return list(views)[rank::world_size]
+
+
+def owner_of(position: int, world_size: int) -> int:
+    """Rank that owns the view at `position` of the sorted view list."""
+    return position % world_size
+
+
+def gather_point_clouds(views: Sequence[int], local: Dict[int, Tuple[torch.Tensor, torch.Tensor]],
+                        device: torch.device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Collect per-view (points (M,3) f64, colors (M,3) u8) on rank 0, concatenated in `views` order.
+
+    `views` is the full sorted list of reference views (identical on every rank); `local` holds this
+    rank's views (those of `shard_views(views)`; a view without points may be missing or empty).
+    Returns the concatenation on rank 0 and empty tensors elsewhere."""
+    rank, ws = world()
+    views = list(views)
+    n = len(views)
+    counts = torch.zeros(n, dtype=torch.int64, device=device)
+    for pos, v in enumerate(views):
+        if owner_of(pos, ws) == rank and v in local:
+            counts[pos] = local[v][0].shape[0]
+    if ws > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)          # every position has exactly one owner
+    counts_h = counts.cpu().tolist()
+
+    def mine(r):
+        return [pos for pos in range(n) if owner_of(pos, ws) == r]
+
+    def pack(r_views):
+        pts = [local[views[p]][0] for p in r_views if counts_h[p] > 0]
+        col = [local[views[p]][1] for p in r_views if counts_h[p] > 0]
+        if not pts:
+            return (torch.zeros((0, 3), dtype=torch.float64, device=device),
+                    torch.zeros((0, 3), dtype=torch.uint8, device=device))
+        return torch.cat(pts).contiguous(), torch.cat(col).contiguous()
+
+    my_pts, my_col = pack(mine(rank))
+    if ws == 1:
+        return my_pts, my_col
+
+    per_rank = {0: (my_pts, my_col)} if rank == 0 else {}
+    ops = []
+    if rank == 0:
+        for r in range(1, ws):
+            m = sum(counts_h[p] for p in mine(r))
+            bp = torch.empty((m, 3), dtype=torch.float64, device=device)
+            bc = torch.empty((m, 3), dtype=torch.uint8, device=device)
+            per_rank[r] = (bp, bc)
+            if m:
+                ops += [dist.P2POp(dist.irecv, bp, r), dist.P2POp(dist.irecv, bc, r)]
+    elif my_pts.shape[0]:
+        ops += [dist.P2POp(dist.isend, my_pts, 0), dist.P2POp(dist.isend, my_col, 0)]
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    if rank != 0:
+        return (torch.zeros((0, 3), dtype=torch.float64, device=device),
+                torch.zeros((0, 3), dtype=torch.uint8, device=device))
+    # re-interleave: position p lives in its owner's buffer after that owner's earlier positions
+    offs = {r: 0 for r in range(ws)}
+    out_p, out_c = [], []
+    for pos in range(n):
+        r, m = owner_of(pos, ws), counts_h[pos]
+        if m:
+            bp, bc = per_rank[r]
+            out_p.append(bp[offs[r]:offs[r] + m])
+            out_c.append(bc[offs[r]:offs[r] + m])
+            offs[r] += m
+    if not out_p:
+        return (torch.zeros((0, 3), dtype=torch.float64, device=device),
+                torch.zeros((0, 3), dtype=torch.uint8, device=device))
+    return torch.cat(out_p), torch.cat(out_c)
+
+
+def all_gather_maps(views: Sequence[int], local: Dict[int, torch.Tensor], shape: Tuple[int, ...],
+                    device: torch.device, dtype=torch.float32) -> Dict[int, torch.Tensor]:
+    """Every rank ends up with the per-view map (e.g. depth (H,W) or normal (H,W,3)) of all views.
+
+    One `all_gather_into_tensor` of a (ceil(n/world), *shape) block per rank (NCCL over NVLink on GPUs);
+    ranks with fewer views pad with zeros."""
+    rank, ws = world()
+    views = list(views)
+    n = len(views)
+    per = (n + ws - 1) // ws
+    block = torch.zeros((per,) + tuple(shape), dtype=dtype, device=device)
+    for k, pos in enumerate(range(rank, n, ws)):
+        v = views[pos]
+        if v in local:
+            block[k].copy_(local[v])
+    if ws == 1:
+        full = block
+    else:
+        full = torch.empty((ws * per,) + tuple(shape), dtype=dtype, device=device)
+        dist.all_gather_into_tensor(full, block)
+    out = {}
+    for pos, v in enumerate(views):
+        out[v] = full[owner_of(pos, ws) * per + pos // ws]
+    return out

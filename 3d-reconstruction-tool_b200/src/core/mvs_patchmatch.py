@@ -55,6 +55,7 @@ class PatchMatchMVS:
         self.seed = seed
         self.device = torch.device(device) if device is not None else torch.device('cuda')
         self.cache_images = True            # keep uploaded grays on the device between views
+        self.views_in_flight = 4            # independent views enqueued concurrently (streams)
         self._engine = None
         self._dev_gray: Dict[int, Tuple[int, torch.Tensor]] = {}
         self._dev_maps: Dict[int, dict] = {}
@@ -87,7 +88,14 @@ class PatchMatchMVS:
     # ------------------------------------------------------------------ public API
     def reconstruct(self, images: List[dict], poses: Dict[int, CameraPose],
                     sparse_points: np.ndarray = None) -> Tuple[np.ndarray, np.ndarray]:
-        """Depth maps for every posed view, fused into one cloud (reference :72-139)."""
+        """Depth maps for every posed view, fused into one cloud (reference :72-139).
+
+        Views are independent, so they are (a) sharded round-robin over the ranks of an initialised
+        torch.distributed job (one process per GPU; without one this is a single-GPU run) and (b) kept
+        `views_in_flight` at a time on separate streams of each GPU.  Rank 0 returns the fused and filtered
+        cloud in the reference's order (sorted views, row-major pixels); other ranks return (0,3) arrays."""
+        from b200dense import dist as bdist
+        rank, ws = bdist.world()
         print("\n" + "=" * 60)
         print("PATCHMATCH MULTI-VIEW STEREO")
         print(f"  Scale: {self.scale}x, Patch: {self.patch_size}, Iters: {self.num_iterations}")
@@ -105,22 +113,43 @@ class PatchMatchMVS:
         proc_images = self._prepare_images(images, cam_indices)
 
         print(f"\nComputing depth maps for {n_cams} views...")
-        depth_maps: Dict[int, DepthNormalMap] = {}
         self._dev_gray.clear()
         self._dev_maps.clear()
-        for i, ref_idx in enumerate(cam_indices):
-            t1 = time.time()
+        eng = self.engine
+        Kinv = np.linalg.inv(self.K_scaled)
+        jobs, job_views = [], []
+        for pos in range(rank, n_cams, ws):
+            ref_idx = cam_indices[pos]
             src_indices = self._select_source_views(ref_idx, cam_indices, poses, k=self.num_src_views)
             if len(src_indices) < 2:
-                print(f"  [{i+1}/{n_cams}] Cam {ref_idx}: skipped (not enough neighbors)")
+                print(f"  [{pos+1}/{n_cams}] Cam {ref_idx}: skipped (not enough neighbors)")
                 continue
-            dm = self._patchmatch_cuda(ref_idx, src_indices, proc_images, poses)
-            depth_maps[ref_idx] = dm
-            valid_pixels = np.sum(dm.confidence >= self.min_views)
-            print(f"  [{i+1}/{n_cams}] Cam {ref_idx}: {valid_pixels:,} valid pixels ({time.time() - t1:.1f}s)")
+
+            def job(slot, ref_idx=ref_idx, src_indices=src_indices):
+                out = self._patchmatch_device(ref_idx, src_indices, proc_images, poses, slot=slot)
+                bgr = eng.to_device(proc_images[ref_idx]['color'], torch.uint8)
+                pts, cols, cnt = eng.mask_backproject(out['depth'], out['confidence'], bgr, Kinv, poses[ref_idx].R,
+                                                      poses[ref_idx].t, float(self.min_views), 0, sync=False, slot=slot)
+                return pts, cols, cnt
+            jobs.append(job)
+            job_views.append((pos, ref_idx))
+        # host-drawn random numbers must be consumed in view order -> one view at a time in that mode
+        results = eng.run_views(jobs, 1 if self.rng == 'torch' else self.views_in_flight)
+        torch.cuda.current_stream().synchronize()
+        local = {}
+        for (pos, ref_idx), (pts, cols, cnt) in zip(job_views, results):
+            m = int(cnt.item())
+            local[ref_idx] = (pts[:m], cols[:m])
+            print(f"  [{pos+1}/{n_cams}] Cam {ref_idx}: {m:,} valid pixels")
 
         print("\nFusing depth maps...")
-        points, colors = self._fuse_depth_maps(depth_maps, proc_images, poses)
+        pts_d, col_d = bdist.gather_point_clouds(cam_indices, local, eng.device)
+        if rank != 0:
+            return np.array([]).reshape(0, 3), np.array([]).reshape(0, 3)
+        if pts_d.shape[0] == 0:
+            points, colors = np.array([]).reshape(0, 3), np.array([]).reshape(0, 3)
+        else:
+            points, colors = pts_d.cpu().numpy(), col_d.cpu().numpy()
         print(f"  Raw points: {len(points):,}")
         if len(points) > 0:
             points, colors = self._filter_points(points, colors)
@@ -203,7 +232,7 @@ class PatchMatchMVS:
         return dict(init_depth=depth0, init_normal=F.normalize(n0, dim=-1), rand_u=ru, rand_n=rn)
 
     def _patchmatch_device(self, ref_idx: int, src_indices: List[int], images: Dict,
-                           poses: Dict[int, CameraPose]) -> dict:
+                           poses: Dict[int, CameraPose], slot: int = 0) -> dict:
         """PatchMatch of one view; returns DEVICE tensors dict(depth, normal, confidence)."""
         eng = self.engine
         ref = self._gray_on_device(images, ref_idx)
@@ -214,7 +243,7 @@ class PatchMatchMVS:
             kw = {k: v.to(eng.device, non_blocking=True).contiguous() for k, v in self._host_rng(H, W).items()}
         return eng.pm_view(ref, srcs, self._camera_block(ref_idx, src_indices, poses), self.patch_size,
                            self.num_iterations, self.num_samples, self.depth_min, self.depth_max,
-                           seed=self.seed, view_id=int(ref_idx), **kw)
+                           seed=self.seed, view_id=int(ref_idx), slot=slot, **kw)
 
     def _patchmatch_cuda(self, ref_idx: int, src_indices: List[int], images: Dict,
                          poses: Dict[int, CameraPose]) -> DepthNormalMap:

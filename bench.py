@@ -183,6 +183,7 @@ def main():
 
     import torch
     import torch.distributed as dist
+    from b200dense import dist as bdist
     from b200dense.engine import DenseEngine, kinv32, make_cams
     from b200dense.scenes import gray_f32
 
@@ -210,21 +211,31 @@ def main():
     outs = {r: dict(depth=torch.empty((H, W), device=dev), normal=torch.empty((H, W, 3), device=dev),
                     confidence=torch.empty((H, W), device=dev)) for r in ref_views}
     NS = max(1, min(a.streams, V))
-    pts_buf = [torch.empty((H * W, 3), dtype=torch.float64, device=dev) for _ in range(NS)]
-    col_buf = [torch.empty((H * W, 3), dtype=torch.uint8, device=dev) for _ in range(NS)]
+    pts_buf = {r: torch.empty((H * W, 3), dtype=torch.float64, device=dev) for r in ref_views}
+    col_buf = {r: torch.empty((H * W, 3), dtype=torch.uint8, device=dev) for r in ref_views}
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+    all_views = sorted(v for rk in range(world) for v in list(range(N_SCENE_VIEWS))[rk::world][:V])
 
     def view_job(r):
         def job(slot):
             o = eng.pm_view(d_gray[r], [d_gray[i] for i in srcs[r]], cams[r], a.patch, a.iters, a.samples, dmin, dmax,
                             seed=1234, view_id=r, out=outs[r], slot=slot)
             return eng.mask_backproject(o['depth'], o['confidence'], d_bgr[r], Kinv64, poses[r].R, poses[r].t, 3.0, 0,
-                                        points=pts_buf[slot], colors=col_buf[slot], sync=False, slot=slot)
+                                        points=pts_buf[r], colors=col_buf[r], sync=False, slot=slot)
         return job
     jobs = [view_job(r) for r in ref_views]
+    gathered = {}
 
     def step():
-        eng.run_views(jobs, NS)
+        res = eng.run_views(jobs, NS)
+        if world > 1:
+            # the job's only exchange: fused clouds of all ranks' views -> rank 0, sorted-view order (NCCL p2p)
+            local = {}
+            for r, (p, c, cnt) in zip(ref_views, res):
+                m = int(cnt.item())
+                local[r] = (p[:m], c[:m])
+            gp, gc = bdist.gather_point_clouds(all_views, local, torch.device(dev))
+            gathered['points'] = int(gp.shape[0])
 
     def barrier():
         if world > 1:
@@ -388,7 +399,8 @@ def main():
             'config': {'workload': workload_name(a), 'views_per_step_per_gpu': V, 'arithmetic': 'parity (bit-exact vs oracle)',
                        'rng': 'philox4x32-10 in-kernel', 'l2': 'flushed between timed steps (512 MiB write)',
                        'views_in_flight': NS,
-                       'parallelism': f'view-sharded dp{world}'},
+                       'parallelism': f'view-sharded dp{world}' + (', fused clouds gathered to rank 0 every step (NCCL p2p)'
+                                                                   if world > 1 else '')},
             'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
             'plane_sweep': sweep}))
     if world > 1:

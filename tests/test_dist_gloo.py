@@ -1,0 +1,79 @@
+"""CPU, world_size 2, gloo: the multi-GPU plumbing (view sharding, ordered point gather, map all-gather).
+The same code runs over NCCL on the GPU box; nothing here needs CUDA."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _fake_cloud(view, n):
+    g = np.random.default_rng(view)
+    return (torch.from_numpy(g.normal(size=(n, 3))), torch.from_numpy(g.integers(0, 255, size=(n, 3)).astype(np.uint8)))
+
+
+VIEWS = [0, 1, 2, 3, 5, 8, 13]                       # 7 views: uneven shards
+COUNTS = {0: 5, 1: 0, 2: 17, 3: 1, 5: 9, 8: 0, 13: 4}  # some views fuse to nothing
+
+
+def _worker(rank, ws, port, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, '3d-reconstruction-tool_b200'))
+    from b200dense import dist as bdist
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=ws)
+    try:
+        mine = bdist.shard_views(VIEWS)
+        assert mine == VIEWS[rank::ws]
+        local = {v: _fake_cloud(v, COUNTS[v]) for v in mine if v != 8}     # view 8 missing entirely
+        pts, col = bdist.gather_point_clouds(VIEWS, local, torch.device('cpu'))
+        maps = bdist.all_gather_maps(VIEWS, {v: torch.full((3, 4), float(v)) for v in mine}, (3, 4), torch.device('cpu'))
+        ok_maps = all(torch.equal(maps[v], torch.full((3, 4), float(v))) for v in VIEWS)
+        q.put((rank, pts.numpy(), col.numpy(), ok_maps))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_gather_point_clouds_and_maps_world2():
+    ws, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, ws, port, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(ws):
+        r, pts, col, ok = q.get(timeout=90)
+        res[r] = (pts, col, ok)
+    for p in procs:
+        p.join(30)
+        assert p.exitcode == 0
+    exp_p = np.concatenate([_fake_cloud(v, COUNTS[v])[0].numpy() for v in VIEWS])
+    exp_c = np.concatenate([_fake_cloud(v, COUNTS[v])[1].numpy() for v in VIEWS])
+    assert np.array_equal(res[0][0], exp_p) and np.array_equal(res[0][1], exp_c)     # sorted-view order on rank 0
+    assert res[1][0].shape == (0, 3) and res[1][1].shape == (0, 3)
+    assert res[0][2] and res[1][2]
+
+
+def test_single_process_paths():
+    import sys
+    from b200dense import dist as bdist
+    assert bdist.world() == (0, 1)
+    assert bdist.shard_views([4, 5, 6], 1, 2) == [5]
+    local = {v: _fake_cloud(v, COUNTS[v]) for v in VIEWS}
+    pts, col = bdist.gather_point_clouds(VIEWS, local, torch.device('cpu'))
+    assert pts.shape[0] == sum(COUNTS.values()) and col.dtype == torch.uint8
+    e, _ = bdist.gather_point_clouds(VIEWS, {}, torch.device('cpu'))
+    assert e.shape == (0, 3)
+    maps = bdist.all_gather_maps([7, 9], {7: torch.ones(2, 2), 9: torch.zeros(2, 2)}, (2, 2), torch.device('cpu'))
+    assert torch.equal(maps[7], torch.ones(2, 2)) and torch.equal(maps[9], torch.zeros(2, 2))
