@@ -195,7 +195,19 @@ def main():
     torch.cuda.set_device(local)
     dev = f'cuda:{local}'
     if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device(dev))
+        # NCCL prints its version banner on stdout when the communicator is created; stdout must carry
+        # exactly one JSON line, so route fd 1 to stderr while the communicator comes up.
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=torch.device(dev))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     eng = DenseEngine(dev)
 
     V, H, W = a.views_per_gpu, a.height, a.width
