@@ -12,7 +12,8 @@ MAX_SRC = 8
 PARITY, FAST = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), 'csrc', 'libb200dense.so')
+# B200DENSE_LIB selects another build of the same ABI (tuning experiments under profiles/microbench)
+LIB_PATH = os.environ.get('B200DENSE_LIB') or os.path.join(os.path.dirname(_HERE), 'csrc', 'libb200dense.so')
 
 
 class Cams(C.Structure):

@@ -73,6 +73,9 @@ struct Geo {
     static constexpr int NL = PX + K - 1;                    // floats per thread per window row
     static constexpr uint32_t tile_bytes = RWP * RH * sizeof(float);
     static constexpr uint32_t buf_bytes = (tile_bytes + 127) / 128 * 128;
+    // Keep this small: 3 CTAs x 38 KB selects the 132 KB shared-memory carve-out and leaves ~96 KB of L1 to the
+    // sampling kernels of other views that share the SM (a 57 KB variant with per-tile statistics in shared memory
+    // forced the 196 KB carve-out and cost 9 % of the concurrent throughput: profiles/r01_notes.md).
     static constexpr size_t smem_bytes = 3 * (size_t)buf_bytes + 64;         // r + 2 stages + barriers
 };
 
@@ -187,9 +190,9 @@ __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_
     using G = Geo<K>;
     constexpr int HALF = G::HALF;
     extern __shared__ __align__(128) unsigned char sm[];     // dynamic smem window starts 128-byte aligned
-    float *s_r = reinterpret_cast<float *>(sm);
-    float *s_buf[2] = {reinterpret_cast<float *>(sm + G::buf_bytes), reinterpret_cast<float *>(sm + 2 * G::buf_bytes)};
-    uint64_t *bar = reinterpret_cast<uint64_t *>(sm + 3 * G::buf_bytes);     // [0],[1]: stages ; [2]: reference
+    constexpr int BUF = G::buf_bytes / sizeof(float);
+    float *s_r = reinterpret_cast<float *>(sm);              // [0,BUF): reference; [BUF,3*BUF): two sample stages
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sm + 3 * G::buf_bytes);   // [0],[1]: stages ; [2]: reference ; [3],[4]: stage released
 
     const int tid = threadIdx.x;
     const int tx = tid % NTX, ty = tid / NTX;
@@ -201,6 +204,8 @@ __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
         mbar_init(&bar[2], 1);
+        mbar_init(&bar[3], NT / 32);                       // one arrival per warp: "stage 0 may be refilled"
+        mbar_init(&bar[4], NT / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -210,18 +215,19 @@ __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_
             tma_load_2d(s_r, &a.tm_r, &bar[2], cx, cy);
         }
         mbar_expect_tx(&bar[0], G::tile_bytes);
-        tma_load_2d(s_buf[0], &a.tm_s[0], &bar[0], cx, cy);
+        tma_load_2d(s_r + BUF, &a.tm_s[0], &bar[0], cx, cy);
         if (S > 1) {
             mbar_expect_tx(&bar[1], G::tile_bytes);
-            tma_load_2d(s_buf[1], &a.tm_s[1], &bar[1], cx, cy);
+            tma_load_2d(s_r + 2 * BUF, &a.tm_s[1], &bar[1], cx, cy);
         }
     }
 
     // per-output constants, issued before the first wait so they are in flight during the TMA
-    float m1[QY][PX], v1[QY][PX], bestv[QY][PX];
-    unsigned vbits[QY][PX];
+    float m1[QY][PX], v1[QY][PX];
+    unsigned vb[QY];                                       // validity bytes of the 4 outputs of a row, packed
 #pragma unroll
-    for (int q = 0; q < QY; ++q)
+    for (int q = 0; q < QY; ++q) {
+        vb[q] = 0;
 #pragma unroll
         for (int p = 0; p < PX; ++p) {
             const int gx = x0 + tx * PX + p, gy = y0 + ty * QY + q;
@@ -229,51 +235,59 @@ __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_
             const size_t g = (size_t)gy * W + gx;
             m1[q][p] = (in && MODE != N_STATS) ? __ldg(a.mean1 + g) : 0.0f;
             v1[q][p] = (in && MODE != N_STATS) ? __ldg(a.var1 + g) : 0.0f;
-            vbits[q][p] = (in && MODE != N_STATS) ? (unsigned)__ldg(a.valid + g) : 0u;
-            bestv[q][p] = (in && (MODE == N_SHIFT || MODE == N_REFINE)) ? a.best_in[g] : 0.0f;
+            vb[q] |= ((in && MODE != N_STATS) ? (unsigned)__ldg(a.valid + g) : 0u) << (8 * p);
         }
+    }
 
-    float as[QY][PX], ass[QY][PX], ars[QY][PX], total[QY][PX], cnt[QY][PX];
+    float as[QY][PX], ass[QY][PX], ars[QY][PX], total[QY][PX];
+    unsigned cnt = 0;                                      // 4-bit valid-source counters of the 8 outputs
 #pragma unroll
     for (int q = 0; q < QY; ++q)
 #pragma unroll
-        for (int p = 0; p < PX; ++p) total[q][p] = cnt[q][p] = 0.0f;
+        for (int p = 0; p < PX; ++p) total[q][p] = 0.0f;
 
+    const int lane = tid & 31;
     if (MODE != N_STATS) mbar_wait(&bar[2], 0);
     for (int s = 0; s < S; ++s) {
         const int st = s & 1;
         mbar_wait(&bar[st], (s >> 1) & 1);
-        box_sums<K>(s_buf[st], (MODE == N_STATS) ? s_buf[st] : s_r, tx, ty, as, ass, ars);
-        __syncthreads();                                   // every thread is done reading stage st
-        if (tid == 0 && s + 2 < S) {
-            mbar_expect_tx(&bar[st], G::tile_bytes);
-            tma_load_2d(s_buf[st], &a.tm_s[s + 2], &bar[st], cx, cy);
-        }
+        box_sums<K>(s_r + (1 + st) * BUF, (MODE == N_STATS) ? s_r + BUF : s_r, tx, ty, as, ass, ars);
         if (MODE == N_STATS) break;
+        if (s + 2 < S) {
+            // release the stage: one arrival per warp; the producer thread refills it once all 8 arrived
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar[3 + st])) : "memory");
+            if (tid == 0) {
+                mbar_wait(&bar[3 + st], (s >> 1) & 1);
+                mbar_expect_tx(&bar[st], G::tile_bytes);
+                tma_load_2d(s_r + (1 + st) * BUF, &a.tm_s[s + 2], &bar[st], cx, cy);
+            }
+        }
 #pragma unroll
         for (int q = 0; q < QY; ++q)
 #pragma unroll
             for (int p = 0; p < PX; ++p) {
+                const float m1v = m1[q][p], v1v = v1[q][p];
                 const float m2 = as[q][p];
                 const float v2 = sub(ass[q][p], mul(m2, m2));
-                const float cov = sub(ars[q][p], mul(m1[q][p], m2));
-                const bool valid = (vbits[q][p] >> s) & 1u;
+                const float cov = sub(ars[q][p], mul(m1v, m2));
+                const bool valid = (vb[q] >> (8 * p + s)) & 1u;
                 if (MODE == N_SWEEP) {
-                    const float ncc = div_(cov, __fsqrt_rn(add(mul(v1[q][p], v2), 1e-8f)));   // dense_stereo.py:344-345
+                    const float ncc = div_(cov, __fsqrt_rn(add(mul(v1v, v2), 1e-8f)));   // dense_stereo.py:344-345
                     if (a.ncc) {
                         const int gx = x0 + tx * PX + p, gy = y0 + ty * QY + q;
                         if (gx < W && gy < H) a.ncc[(((size_t)a.plane * S + s) * H + gy) * W + gx] = ncc;
                     }
                     if ((ncc > a.thresh) && valid) total[q][p] = add(total[q][p], 1.0f);      // :303-304
                 } else {
-                    const float ncc = div_(cov, add(__fsqrt_rn(mul(v1[q][p], v2)), 1e-8f));   // mvs_patchmatch.py:410
+                    const float ncc = div_(cov, add(__fsqrt_rn(mul(v1v, v2)), 1e-8f));   // mvs_patchmatch.py:410
                     const float cost = sub(1.0f, ncc);
                     if (MODE == N_CONF) {
                         const float ncc2 = sub(1.0f, cost);                                   // :530
                         if (valid && (ncc2 > 0.6f)) total[q][p] = add(total[q][p], 1.0f);
                     } else {
                         total[q][p] = add(total[q][p], valid ? cost : 0.0f);                  // :383
-                        cnt[q][p] = add(cnt[q][p], valid ? 1.0f : 0.0f);
+                        cnt += valid ? (1u << (4 * (q * PX + p))) : 0u;
                     }
                 }
             }
@@ -306,11 +320,12 @@ __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_
                 if (a.plane == a.n_planes - 1) a.depth_map[g] = __ldg(a.depths + bi);          // :310
                 continue;
             }
-            const float avg = div_(total[q][p], add(cnt[q][p], 1e-8f));                       // :387
-            const float cost = (cnt[q][p] >= 2.0f) ? avg : __int_as_float(0x7f800000);       // :388
+            const float cntf = (float)((cnt >> (4 * (q * PX + p))) & 15u);
+            const float avg = div_(total[q][p], add(cntf, 1e-8f));                            // :387
+            const float cost = (cntf >= 2.0f) ? avg : __int_as_float(0x7f800000);            // :388
             if (a.out) a.out[g] = cost;
             if (MODE == N_COST) continue;
-            const float best = bestv[q][p];
+            const float best = a.best_in[g];
             const bool better = cost < best;                                                  // strict; NaN never wins
             float n0, n1, n2;
             if (better) {
