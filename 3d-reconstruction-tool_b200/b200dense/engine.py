@@ -7,6 +7,7 @@ There is no CPU path: constructing a DenseEngine without CUDA raises.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -38,6 +39,32 @@ def make_cams(K_scaled, Kinv32, R_ref, t_ref, R_src: Sequence, t_src: Sequence) 
         c.R_src[s][:] = np.asarray(R, dtype=np.float64).astype(f).ravel().tolist()
         c.t_src[s][:] = np.asarray(t, dtype=np.float64).astype(f).ravel().tolist()
     return c
+
+
+class PinnedPool:
+    """Recycles page-locked staging buffers for device->host results.
+
+    Page-locking a fresh 23 MB buffer costs ~12 ms on the B200 hosts (measured, profiles/microbench/dbg_e2e.py) --
+    more than the PatchMatch of the view it carries -- so buffers are pooled by (shape, dtype).  A result array
+    handed to the caller owns its buffer; when the array is garbage-collected the buffer returns to the pool."""
+
+    def __init__(self):
+        self._free: Dict[Tuple[Tuple[int, ...], torch.dtype], List[torch.Tensor]] = {}
+
+    def take(self, shape, dtype) -> torch.Tensor:
+        lst = self._free.get((tuple(shape), dtype))
+        return lst.pop() if lst else torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+
+    def _give(self, t: torch.Tensor) -> None:
+        self._free.setdefault((tuple(t.shape), t.dtype), []).append(t)
+
+    def as_numpy(self, t: torch.Tensor) -> np.ndarray:
+        a = t.numpy()
+        weakref.finalize(a, self._give, t)
+        return a
+
+
+PINNED = PinnedPool()
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -88,15 +115,14 @@ class DenseEngine:
 
     @staticmethod
     def to_host(ts: Sequence[torch.Tensor]) -> List[np.ndarray]:
-        """Device tensors -> fresh host arrays through pinned staging (torch's caching host allocator
-        recycles the pinned blocks, so this is one DMA per tensor and one synchronisation in total)."""
+        """Device tensors -> host arrays in pooled page-locked buffers: one DMA per tensor, one synchronisation."""
         hs = []
         for t in ts:
-            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h = PINNED.take(t.shape, t.dtype)
             h.copy_(t, non_blocking=True)
             hs.append(h)
         torch.cuda.current_stream().synchronize()
-        return [h.numpy() for h in hs]
+        return [PINNED.as_numpy(h) for h in hs]
 
     # ------------------------------------------------------------------ concurrent views
     def run_views(self, jobs: Sequence, n_streams: int = 4) -> list:

@@ -245,6 +245,56 @@ class PatchMatchMVS:
                            self.num_iterations, self.num_samples, self.depth_min, self.depth_max,
                            seed=self.seed, view_id=int(ref_idx), slot=slot, **kw)
 
+    def compute_depth_maps(self, images: Dict, poses: Dict[int, CameraPose], ref_indices: List[int] = None,
+                           sources: Dict[int, List[int]] = None) -> Dict[int, DepthNormalMap]:
+        """Batch form of `_patchmatch_cuda`: host grays in, host maps out, for many reference views at once.
+
+        `images` is the dict `_prepare_images` returns.  Every distinct gray is uploaded once per call, the views
+        run `views_in_flight` at a time on separate streams, and each view's depth / normal / confidence come back
+        through pinned staging on its own stream, so copies overlap the other views' kernels.  This is what
+        `reconstruct()` does internally; views with fewer than two sources are skipped like there (:110-112)."""
+        from b200dense.engine import PINNED
+        eng = self.engine
+        all_indices = sorted(poses.keys())
+        ref_indices = list(all_indices if ref_indices is None else ref_indices)
+        plan = []
+        for r in ref_indices:
+            src = sources[r] if sources is not None else self._select_source_views(r, all_indices, poses,
+                                                                                   k=self.num_src_views)
+            if len(src) >= 2:
+                plan.append((r, list(src)))
+        keep = self.cache_images
+        self.cache_images = True
+        if not keep:
+            self._dev_gray.clear()                       # re-upload: the caller asked for no caching across calls
+        try:
+            for i in sorted({i for r, src in plan for i in [r] + src}):
+                self._gray_on_device(images, i)
+            jobs = []
+            for r, src in plan:
+                def job(slot, r=r, src=src):
+                    out = self._patchmatch_device(r, src, images, poses, slot=slot)
+                    host = []
+                    for k in ('depth', 'normal', 'confidence'):
+                        h = PINNED.take(out[k].shape, out[k].dtype)
+                        h.copy_(out[k], non_blocking=True)
+                        host.append(h)
+                    return out, host
+                jobs.append(job)
+            results = eng.run_views(jobs, 1 if self.rng == 'torch' else self.views_in_flight)
+            torch.cuda.current_stream().synchronize()
+        finally:
+            self.cache_images = keep
+            if not keep:
+                self._dev_gray.clear()
+        maps = {}
+        for (r, _), (out, host) in zip(plan, results):
+            dm = DepthNormalMap(depth=PINNED.as_numpy(host[0]), normal=PINNED.as_numpy(host[1]),
+                                confidence=PINNED.as_numpy(host[2]))
+            self._dev_maps[r] = dict(owner=id(dm.depth), depth=out['depth'], confidence=out['confidence'])
+            maps[r] = dm
+        return maps
+
     def _patchmatch_cuda(self, ref_idx: int, src_indices: List[int], images: Dict,
                          poses: Dict[int, CameraPose]) -> DepthNormalMap:
         """Same seam as the reference's `_patchmatch_cuda` (:225-321): host grays in, host maps out."""

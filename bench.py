@@ -12,8 +12,9 @@ back-projection of every view -- the per-GPU share of BASELINE.json configs[3]. 
 V views.  Arithmetic: the bit-exact parity kernels (the ones the parity tests gate).
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs in HBM), `e2e` goes
-through the reference-facing `PatchMatchMVS._patchmatch_cuda` with pinned HOST buffers (H2D of the 6
-grays and D2H of depth/normal/confidence per view inside the timed region).
+through the reference-facing `PatchMatchMVS.compute_depth_maps` (batch form of `_patchmatch_cuda`) with pinned
+HOST buffers: H2D of every gray the step touches and D2H of depth/normal/confidence of every view inside the
+timed region.
 """
 import argparse
 import json
@@ -341,21 +342,24 @@ def main():
         proc = {i: {'gray': pinned[i].numpy(), 'shape': (H, W)} for i in need}
 
         def step_e2e():
-            for r in ref_views:
-                dm = pm._patchmatch_cuda(r, srcs[r], proc, poses)
-                assert dm.depth.shape == (H, W)
-        step_e2e()
+            maps = pm.compute_depth_maps(proc, poses, ref_views, srcs)
+            assert len(maps) == V and maps[ref_views[0]].depth.shape == (H, W)
+        for _ in range(2):
+            step_e2e()
         barrier()
         t0 = time.perf_counter()
         for _ in range(a.steps):
+            ts = time.perf_counter()
             step_e2e()
+            print(f'[e2e] step {1e3 * (time.perf_counter() - ts):.1f} ms', file=sys.stderr)
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {'value': V * world * a.steps / float(dt.item()), 'unit': UNIT,
-               'h2d_bytes_per_step': V * (1 + a.src) * H * W * 4, 'd2h_bytes_per_step': V * 5 * H * W * 4,
-               'api': 'core.mvs_patchmatch.PatchMatchMVS._patchmatch_cuda (host grays in, host maps out)'}
+               'h2d_bytes_per_step': len(need) * H * W * 4, 'd2h_bytes_per_step': V * 5 * H * W * 4,
+               'api': 'core.mvs_patchmatch.PatchMatchMVS.compute_depth_maps (batch form of _patchmatch_cuda: pinned host '
+                      'grays in, every distinct image uploaded once per step, host depth/normal/confidence out)'}
 
     # ---- secondary metric: plane sweep Gpix*planes/s (BASELINE configs[2] shape, one view per GPU)
     sweep = None

@@ -105,3 +105,26 @@ def test_fewer_than_two_neighbours_skips_view_and_wrapper():
     assert p.shape == (0, 3) and c.shape == (0, 3)
     p, c = create_combined_dense_cloud(cam, images, poses, use_stereo=False)
     assert len(p) == 0
+
+
+def test_compute_depth_maps_equals_per_view_calls():
+    """The batched host API returns exactly what `_patchmatch_cuda` returns view by view."""
+    from b200dense.scenes import make_scene
+    sc = make_scene('wavy', 6, 150, 90, seed=31)
+    cam = Camera(K=sc.K.copy(), dist=np.zeros(5))
+    poses = {i: CameraPose(R=sc.poses[i][0], t=sc.poses[i][1]) for i in sc.poses}
+    pm = PatchMatchMVS(cam, scale=1.0, patch_size=5, num_iterations=2, num_samples=2, seed=9, num_src_views=3)
+    pm.depth_min, pm.depth_max = sc.depth_range
+    proc = pm._prepare_images(sc.images, sorted(poses))
+    srcs = {r: [i for i in sorted(poses) if i != r][:3] for r in sorted(poses)}
+    for cache in (True, False):
+        pm.cache_images = cache
+        batch = pm.compute_depth_maps(proc, poses, [0, 2, 5], srcs)
+        assert sorted(batch) == [0, 2, 5]
+        for r in (0, 2, 5):
+            one = pm._patchmatch_cuda(r, srcs[r], proc, poses)
+            assert np.array_equal(batch[r].depth, one.depth)
+            assert np.array_equal(batch[r].normal, one.normal)
+            assert np.array_equal(batch[r].confidence, one.confidence)
+    pts, col = pm._fuse_depth_maps(batch, proc, poses)
+    assert pts.shape[1] == 3 and len(pts) == len(col)
