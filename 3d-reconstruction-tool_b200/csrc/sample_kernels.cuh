@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(SBX *SBY) sample_kernel(const __grid_constant_
 
     float pw[3];
     backproject_world(a.cams, (float)x, (float)y, cd, pw);
-    const Rcp rw = make_rcp((float)(W - 1)), rh = make_rcp((float)(H - 1));
+    const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+    const float rw = rcp_refined(wm1), rh = rcp_refined(hm1);
     const float lo = (BOUNDS == B_PATCH) ? (float)a.half : 0.0f;
     const float hix = (BOUNDS == B_PATCH) ? (float)(W - a.half) : (float)W;
     const float hiy = (BOUNDS == B_PATCH) ? (float)(H - a.half) : (float)H;
@@ -85,12 +86,17 @@ __global__ void __launch_bounds__(SBX *SBY) sample_kernel(const __grid_constant_
     const int S = a.cams.n_src;
 #pragma unroll 2
     for (int s = 0; s < S; ++s) {
-        float u, v, z;
-        project_src(a.cams, s, pw, u, v, z);
+        float u, v, z, smp;
+        if (!project_sample_fast(a.cams, s, pw, a.src[s], W, wm1, hm1, rw, rh, u, v, z, smp)) {
+            float uv[2];
+            smp = project_sample_exact(a.cams, s, pw, a.src[s], W, wm1, hm1, uv);
+            u = uv[0];
+            v = uv[1];
+        }
         bool ok = z > 0.1f;
-        if (BOUNDS != B_DEPTH) ok = ok && (u >= lo) && (u < hix) && (v >= lo) && (v < hiy);
-        vmask |= ok ? (1u << s) : 0u;
-        out[(size_t)s * a.map_stride] = sample_bilinear(a.src[s], W, rw, rh, u, v);
+        if (BOUNDS != B_DEPTH) ok = ok & (u >= lo) & (u < hix) & (v >= lo) & (v < hiy);
+        vmask |= (unsigned)ok << s;
+        out[(size_t)s * a.map_stride] = smp;
     }
     if (a.cand) a.cand[g] = cd;
     a.valid[g] = (uint8_t)vmask;

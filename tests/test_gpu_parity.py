@@ -147,3 +147,29 @@ def test_unsupported_arguments_raise(engine):
         engine.ref_stats(x, 4)
     with pytest.raises(B200DenseError):
         engine.ref_stats(x, 15)
+
+
+def test_exact_division_fallback_paths(engine):
+    """Operands outside the range where the shared-reciprocal division is trusted (zero numerators at the
+    principal point, z + 1e-8 near zero, huge / tiny / negative / inf / NaN depths) must take the exact
+    twin and still match the oracle bit for bit."""
+    from b200dense.engine import make_cams
+    H, W, k = 48, 64, 5
+    rng = np.random.default_rng(3)
+    K = np.array([[50.0, 0, 32.0], [0, 50.0, 24.0], [0, 0, 1.0]])          # integer principal point -> exact zeros
+    Ki = np.linalg.inv(K).astype(np.float32)
+    I3 = np.eye(3)
+    R = [I3, I3, I3, I3]
+    t = [np.zeros(3), np.array([0.0, 0.0, -2.0]), np.array([0.0, 0.0, 1.0]), np.array([0.25, 0.0, 0.0])]
+    gray = [rng.random((H, W), dtype=np.float32) for _ in range(4)]
+    depth = rng.uniform(1.0, 4.0, size=(H, W)).astype(np.float32)
+    depth[0, :8] = [0.0, 1e-30, 1e30, -3.0, np.inf, np.nan, 2.0, 1e-12]
+    depth[10:20, :] = 2.0                                                    # z = 2 - 2 = 0 in source 1: zz = 1e-8
+    depth[24, 32] = 1.0                                                      # principal point: numerators exactly 0
+    src = [1, 2, 3]
+    ocams = orc.Cams(K, Ki, R[0], t[0], [R[i] for i in src], [t[i] for i in src])
+    ecams = make_cams(K, Ki, R[0], t[0], [R[i] for i in src], [t[i] for i in src])
+    for mode in (0, 1):
+        got = engine.pm_cost(dev(engine, gray[0]), [dev(engine, gray[i]) for i in src], ecams, dev(engine, depth), k, mode)
+        exp = orc.pm_cost(gray[0], [gray[i] for i in src], ocams, depth, k, mode)
+        assert np.array_equal(got.cpu().numpy(), exp, equal_nan=True), f'mode {mode}'
