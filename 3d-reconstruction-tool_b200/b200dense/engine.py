@@ -233,6 +233,16 @@ class DenseEngine:
         self.launches += 1 + 2 * D
         return dict(depth_map=depth_map, confidence=conf, best_idx=idx, ncc=ncc)
 
+    def geo_consistency(self, depth_ref: torch.Tensor, depth_srcs: Sequence[torch.Tensor], cams: Cams,
+                        px_thresh: float = 1.0, rel_thresh: float = 0.01) -> torch.Tensor:
+        """EXTENSION: number of source views whose depth map agrees geometrically with `depth_ref` (H,W)."""
+        H, W = depth_ref.shape
+        out = torch.empty_like(depth_ref)
+        _cabi.check(self.lib.b200d_geo_consistency(_ptr(depth_ref), _ptr_array(depth_srcs), C.byref(cams), H, W,
+                                                   float(px_thresh), float(rel_thresh), _ptr(out), self._stream()))
+        self.launches += 1
+        return out
+
     def mask_backproject(self, depth: torch.Tensor, conf: torch.Tensor, bgr: torch.Tensor, Kinv64: np.ndarray,
                          R: np.ndarray, t: np.ndarray, min_conf: float, mode: int,
                          points: Optional[torch.Tensor] = None, colors: Optional[torch.Tensor] = None,

@@ -13,6 +13,7 @@
 
 #include "b200dense.h"
 #include "fuse_kernels.cuh"
+#include "geo_kernels.cuh"
 #include "ncc_kernels.cuh"
 #include "sample_kernels.cuh"
 
@@ -462,6 +463,25 @@ int b200d_plane_sweep(const float *d_ref, const float *const *d_nbr, const b200d
         TRY(launch_ncc_k<N_SWEEP>(patch, a, st));
     }
     return B200D_OK;
+}
+
+int b200d_geo_consistency(const float *d_depth_ref, const float *const *d_depth_src, const b200d_cams *cams, int H, int W,
+                           float px_thresh, float rel_thresh, float *d_count, void *stream) {
+    TRY(check_cams(cams));
+    if (H < 1 || W < 1) return fail(B200D_ERR_ARG, "empty image");
+    if (!d_depth_ref || !d_depth_src || !d_count) return fail(B200D_ERR_ARG, "null pointer");
+    GeoArgs a;
+    memset(&a, 0, sizeof(a));
+    a.depth_ref = d_depth_ref;
+    for (int s = 0; s < cams->n_src; ++s) {
+        if (!d_depth_src[s]) return fail(B200D_ERR_ARG, "null pointer");
+        a.depth_src[s] = d_depth_src[s];
+    }
+    a.cams = *cams; a.H = H; a.W = W; a.px_thresh = px_thresh; a.rel_thresh = rel_thresh; a.out = d_count;
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(5000, st);
+    geo_consistency_kernel<<<dim3((W + 31) / 32, (H + 7) / 8, 1), dim3(32, 8, 1), 0, st>>>(a);
+    return cuda_check(cudaGetLastError(), "geo_consistency_kernel launch");
 }
 
 int b200d_mask_backproject(const float *d_depth, const float *d_conf, const uint8_t *d_bgr, int H, int W,

@@ -32,6 +32,7 @@ class DenseStereoReconstructor:
         self.num_neighbors = num_neighbors
         self.device = torch.device(device) if device is not None else torch.device('cuda')
         self._engine = None
+        self.views_in_flight = 2            # independent reference views enqueued concurrently (streams)
         self._dev_gray: Dict[int, Tuple[int, torch.Tensor]] = {}
         if torch.cuda.is_available():
             print(f"Dense stereo using GPU: {torch.cuda.get_device_name()}")
@@ -83,20 +84,38 @@ class DenseStereoReconstructor:
         step = max(1, n_cameras // max_pairs)                    # reference :100-101
         ref_indices = camera_indices[::step]
         print(f"\nProcessing {len(ref_indices)} reference views...")
-        all_points, all_colors = [], []
-        for i, ref_idx in enumerate(ref_indices):
-            t1 = time.time()
+        # Reference views are independent: shard them round-robin over the ranks of an initialised
+        # torch.distributed job and keep `views_in_flight` of this rank's views on separate streams.
+        from b200dense import dist as bdist
+        rank, ws = bdist.world()
+        eng = self.engine
+        Kinv = np.linalg.inv(self.K_scaled)
+        jobs, job_views = [], []
+        for pos in range(rank, len(ref_indices), ws):
+            ref_idx = ref_indices[pos]
             neighbors = self._find_neighbors(ref_idx, camera_indices, poses, k=self.num_neighbors)
             if len(neighbors) < 2:
                 continue
-            depth_map, confidence, color_map = self._compute_depth_map_gpu(
-                ref_idx, neighbors, processed, poses, depth_min, depth_max)
-            points, colors = self._backproject(depth_map, confidence, color_map, poses[ref_idx],
-                                               min_confidence=self.min_views - 0.5)
-            if len(points) > 0:
-                all_points.append(points)
-                all_colors.append(colors)
-            print(f"  [{i+1}/{len(ref_indices)}] Cam {ref_idx}: {len(points):,} pts ({time.time() - t1:.1f}s)")
+
+            def job(slot, ref_idx=ref_idx, neighbors=neighbors):
+                out = self._sweep_device(ref_idx, neighbors, processed, poses, depth_min, depth_max, slot=slot)
+                bgr = eng.to_device(processed[ref_idx]['color'], torch.uint8)
+                return eng.mask_backproject(out['depth_map'], out['confidence'], bgr, Kinv, poses[ref_idx].R,
+                                            poses[ref_idx].t, float(self.min_views - 0.5), 1, sync=False, slot=slot)
+            jobs.append(job)
+            job_views.append((pos, ref_idx))
+        results = eng.run_views(jobs, self.views_in_flight)
+        torch.cuda.current_stream().synchronize()
+        local = {}
+        for (pos, ref_idx), (pts, cols, cnt) in zip(job_views, results):
+            m = int(cnt.item())
+            local[ref_idx] = (pts[:m], cols[:m])
+            print(f"  [{pos+1}/{len(ref_indices)}] Cam {ref_idx}: {m:,} pts")
+        pts_d, col_d = bdist.gather_point_clouds(ref_indices, local, eng.device)
+        if rank != 0:
+            return np.array([]), np.array([])
+        all_points = [pts_d.cpu().numpy()] if pts_d.shape[0] else []
+        all_colors = [col_d.cpu().numpy()] if pts_d.shape[0] else []
 
         if not all_points:
             print("No points reconstructed!")
@@ -150,7 +169,7 @@ class DenseStereoReconstructor:
         out = self._sweep_device(ref_idx, neighbor_indices, processed, poses, depth_min, depth_max)
         return out['depth_map'].cpu().numpy(), out['confidence'].cpu().numpy(), processed[ref_idx]['color']
 
-    def _sweep_device(self, ref_idx, neighbor_indices, processed, poses, depth_min, depth_max) -> dict:
+    def _sweep_device(self, ref_idx, neighbor_indices, processed, poses, depth_min, depth_max, slot: int = 0) -> dict:
         from b200dense.engine import kinv32, make_cams
         eng = self.engine
         cams = make_cams(self.K_scaled, kinv32(self.K_scaled), poses[ref_idx].R, poses[ref_idx].t,
@@ -158,7 +177,7 @@ class DenseStereoReconstructor:
         depths = self._plane_depths(depth_min, depth_max).astype(np.float32)
         return eng.plane_sweep(self._gray_on_device(processed, ref_idx),
                                [self._gray_on_device(processed, i) for i in neighbor_indices], cams, depths,
-                               self.patch_size, self.consistency_thresh)
+                               self.patch_size, self.consistency_thresh, slot=slot)
 
     def _backproject(self, depth_map: np.ndarray, confidence: np.ndarray, color_map: np.ndarray,
                      pose: CameraPose, min_confidence: float) -> Tuple[np.ndarray, np.ndarray]:

@@ -39,7 +39,9 @@ class DepthNormalMap:
 class PatchMatchMVS:
     def __init__(self, camera: Camera, scale: float = 0.25, patch_size: int = 11, num_iterations: int = 3,
                  num_samples: int = 8, min_views: int = 3, depth_min: float = 0.1, depth_max: float = 100.0,
-                 *, num_src_views: int = 4, rng: str = 'philox', seed: int = 0, device=None):
+                 *, num_src_views: int = 4, rng: str = 'philox', seed: int = 0, device=None,
+                 consistency: str = 'photometric', geo_min_views: int = 2, geo_px_thresh: float = 1.0,
+                 geo_rel_thresh: float = 0.01):
         self.camera = camera
         self.scale = scale
         self.patch_size = patch_size
@@ -53,6 +55,10 @@ class PatchMatchMVS:
             raise ValueError("rng must be 'philox' or 'torch'")
         self.rng = rng
         self.seed = seed
+        if consistency not in ('photometric', 'geometric'):
+            raise ValueError("consistency must be 'photometric' (the reference's check) or 'geometric' (extension)")
+        self.consistency = consistency
+        self.geo_min_views, self.geo_px_thresh, self.geo_rel_thresh = geo_min_views, geo_px_thresh, geo_rel_thresh
         self.device = torch.device(device) if device is not None else torch.device('cuda')
         self.cache_images = True            # keep uploaded grays on the device between views
         self.views_in_flight = 4            # independent views enqueued concurrently (streams)
@@ -124,23 +130,40 @@ class PatchMatchMVS:
             if len(src_indices) < 2:
                 print(f"  [{pos+1}/{n_cams}] Cam {ref_idx}: skipped (not enough neighbors)")
                 continue
-
-            def job(slot, ref_idx=ref_idx, src_indices=src_indices):
-                out = self._patchmatch_device(ref_idx, src_indices, proc_images, poses, slot=slot)
-                bgr = eng.to_device(proc_images[ref_idx]['color'], torch.uint8)
-                pts, cols, cnt = eng.mask_backproject(out['depth'], out['confidence'], bgr, Kinv, poses[ref_idx].R,
-                                                      poses[ref_idx].t, float(self.min_views), 0, sync=False, slot=slot)
-                return pts, cols, cnt
-            jobs.append(job)
-            job_views.append((pos, ref_idx))
+            jobs.append(lambda slot, r=ref_idx, s=src_indices: self._patchmatch_device(r, s, proc_images, poses, slot=slot))
+            job_views.append((pos, ref_idx, src_indices))
         # host-drawn random numbers must be consumed in view order -> one view at a time in that mode
         results = eng.run_views(jobs, 1 if self.rng == 'torch' else self.views_in_flight)
-        torch.cuda.current_stream().synchronize()
+        maps = {ref_idx: out for (_, ref_idx, _), out in zip(job_views, results)}
+
+        if self.consistency == 'geometric':
+            # EXTENSION (no reference counterpart): cross-view geometric check.  The depth maps of the other ranks'
+            # views arrive by one NCCL all-gather; the check itself is again view-local.
+            H, W = next(iter(proc_images.values()))['shape']
+            all_depth = bdist.all_gather_maps(cam_indices, {v: o['depth'] for v, o in maps.items()}, (H, W), eng.device)
+            computed = bdist.all_gather_maps(cam_indices, {v: torch.ones(1, device=eng.device) for v in maps}, (1,),
+                                             eng.device)
+            for _, ref_idx, src_indices in job_views:
+                srcs = [i for i in src_indices if float(computed[i].item()) > 0]
+                if not srcs:
+                    maps[ref_idx]['confidence'].zero_()
+                    continue
+                from b200dense.engine import kinv32, make_cams
+                cams = make_cams(self.K_scaled, kinv32(self.K_scaled), poses[ref_idx].R, poses[ref_idx].t,
+                                 [poses[i].R for i in srcs], [poses[i].t for i in srcs])
+                geo = eng.geo_consistency(maps[ref_idx]['depth'], [all_depth[i].contiguous() for i in srcs], cams,
+                                          self.geo_px_thresh, self.geo_rel_thresh)
+                conf = maps[ref_idx]['confidence']
+                maps[ref_idx]['confidence'] = torch.where(geo >= float(self.geo_min_views), conf, torch.zeros_like(conf))
+
         local = {}
-        for (pos, ref_idx), (pts, cols, cnt) in zip(job_views, results):
-            m = int(cnt.item())
-            local[ref_idx] = (pts[:m], cols[:m])
-            print(f"  [{pos+1}/{n_cams}] Cam {ref_idx}: {m:,} valid pixels")
+        for pos, ref_idx, _ in job_views:
+            out = maps[ref_idx]
+            bgr = eng.to_device(proc_images[ref_idx]['color'], torch.uint8)
+            pts, cols = eng.mask_backproject(out['depth'], out['confidence'], bgr, Kinv, poses[ref_idx].R,
+                                             poses[ref_idx].t, float(self.min_views), 0)
+            local[ref_idx] = (pts.clone(), cols.clone())
+            print(f"  [{pos+1}/{n_cams}] Cam {ref_idx}: {pts.shape[0]:,} valid pixels")
 
         print("\nFusing depth maps...")
         pts_d, col_d = bdist.gather_point_clouds(cam_indices, local, eng.device)

@@ -146,6 +146,14 @@ B200D_API int b200d_mask_backproject(const float *d_depth, const float *d_conf, 
                            float min_conf, int mode, double *d_points, uint8_t *d_colors,
                            int64_t *d_count, void *d_scratch, void *stream);
 
+/* EXTENSION (no counterpart in the reference, whose consistency check is photometric -- SURVEY F6): cross-view
+ * geometric consistency.  For every reference pixel: back-project at d_depth_ref, project into each source,
+ * read that source's depth map at the nearest pixel, back-project, return to the reference camera; a source is
+ * consistent when the round trip lands within px_thresh pixels and rel_thresh relative depth.  d_count (H,W)
+ * receives the number of consistent sources.  cams: K, R_ref/t_ref and the sources' R/t (Kinv unused). */
+B200D_API int b200d_geo_consistency(const float *d_depth_ref, const float *const *d_depth_src, const b200d_cams *cams,
+                                    int H, int W, float px_thresh, float rel_thresh, float *d_count, void *stream);
+
 /* Optional per-launch timing for benchmarks.  Between _begin and _end every tile kernel launched by
  * this library is bracketed by CUDA events on its own stream (library-owned events, at most
  * max_records launches).  _end waits for the recorded launches, writes their durations (ms) and tags
