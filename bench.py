@@ -51,6 +51,7 @@ def parse():
     ap.add_argument('--iters', type=int, default=3)
     ap.add_argument('--samples', type=int, default=8)
     ap.add_argument('--streams', type=int, default=4, help='independent views in flight per GPU')
+    ap.add_argument('--sweep-streams', type=int, default=2, help='plane-sweep reference views in flight per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-plane-sweep', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
@@ -366,32 +367,38 @@ def main():
     if not a.no_plane_sweep:
         from b200dense.scenes import make_scene
         Ws, Hs, D, N, k = 1920, 1080, 256, 6, 7
-        nb_views = [0, 1, 2, 3, 4, 5, 6]
+        nb_views = list(range(0, 10))
         scs = make_scene('turntable', N_SCENE_VIEWS, Ws, Hs, arc_deg=360.0 / N_SCENE_VIEWS, seed=0, device=dev, render=nb_views)
         gs = gray_f32(scs)
-        dg = [eng.to_device(gs[i]) for i in nb_views]
-        ref_i, nbs = 3, [2, 4, 1, 5, 0, 6]
-        cs = make_cams(scs.K, kinv32(scs.K), scs.poses[ref_i][0], scs.poses[ref_i][1], [scs.poses[i][0] for i in nbs],
-                       [scs.poses[i][1] for i in nbs])
+        dg = {i: eng.to_device(gs[i]) for i in nb_views}
+        refs_s = [3, 4, 5, 6]                                  # 4 reference views per rep, 2 in flight
         depths = (1.0 / np.linspace(1 / scs.depth_range[1], 1 / scs.depth_range[0], D)).astype(np.float32)
-        for _ in range(2):
-            eng.plane_sweep(dg[ref_i], [dg[i] for i in nbs], cs, depths, k, 0.8)
+        Ki = kinv32(scs.K)
+
+        def sweep_job(r):
+            nbs = [r - 1, r + 1, r - 2, r + 2, r - 3, r + 3]   # 6 nearest cameras on the circle
+            cs = make_cams(scs.K, Ki, scs.poses[r][0], scs.poses[r][1], [scs.poses[i][0] for i in nbs],
+                           [scs.poses[i][1] for i in nbs])
+            return lambda slot: eng.plane_sweep(dg[r], [dg[i] for i in nbs], cs, depths, k, 0.8, slot=slot)
+        sjobs = [sweep_job(r) for r in refs_s]
+        eng.run_views(sjobs[:2], a.sweep_streams)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 3
         e0.record()
-        for _ in range(reps):
-            eng.plane_sweep(dg[ref_i], [dg[i] for i in nbs], cs, depths, k, 0.8)
+        eng.run_views(sjobs, a.sweep_streams)
         e1.record()
         barrier()
         tms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        gpp = world * reps * Hs * Ws * D / (float(tms.item()) / 1e3) / 1e9
+        gpp = world * len(refs_s) * Hs * Ws * D / (float(tms.item()) / 1e3) / 1e9
         sweep = {'metric': 'plane_sweep_gpix_planes_per_s', 'value': gpp, 'unit': 'Gpix*planes/s',
-                 'config': f'{Ws}x{Hs}, D={D}, N={N}, {k}x{k} NCC, 1 ref view per GPU per rep, parity arithmetic',
-                 'ms_per_view': float(tms.item()) / reps,
-                 'fp32_frac_fast_model': gpp * 1e9 * N * (40 + 6 * (k - 1)) / world / (148 * 128 * 1965e6)}
+                 'config': f'{Ws}x{Hs}, D={D}, N={N}, {k}x{k} NCC, {len(refs_s)} ref views per GPU ({a.sweep_streams} in flight), '
+                           f'parity arithmetic (BASELINE configs[2] shape)',
+                 'ms_per_view': float(tms.item()) / len(refs_s),
+                 'evals_per_s': gpp * 1e9 * N,
+                 'fp32_frac_parity_model': gpp * 1e9 * N * (40 + 3 * k * k) / world / 36.3e12,
+                 'fp32_frac_fast_model': gpp * 1e9 * N * (40 + 6 * (k - 1)) / world / 36.3e12}
 
     # ---- CPU baseline on the box's host cores (rank 0, N=1 only): the oracle on a bounded sample
     cpu = None

@@ -55,11 +55,14 @@ def run(libpath):
     nb = [im2[i] for i in (2, 4, 1, 5, 0, 6)]
     eng.plane_sweep(im2[3], nb, cams2, depths, 7, 0.8)
     torch.cuda.synchronize()
+    eng.profile_begin(4096)
     e0.record()
     eng.plane_sweep(im2[3], nb, cams2, depths, 7, 0.8)
     e1.record()
     torch.cuda.synchronize()
+    ms2, tags2 = eng.profile_end()
     sw = e0.elapsed_time(e1)
+    print('   sweep per-plane: sample', float(ms2[tags2 == 2032].mean()), 'ncc', float(ms2[tags2 == 507].mean()))
     print(f"{os.path.basename(libpath):40s} view {view_ms:7.3f} ms  ncc-refine {out.get(411, 0):.4f}  sample-refine {out.get(2020, 0):.4f}  ncc-shift {out.get(311, 0):.4f}  "
           f"sample-shift {out.get(2010, 0):.4f}  stats {out.get(11, 0):.4f}   sweep(D=64) {sw:7.2f} ms = {Hs * Ws * 64 / sw / 1e6:.2f} Gpix*planes/s")
 

@@ -20,7 +20,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _run(rank, ws, port, q):
+def _run(rank, ws, port, q, mode='photometric'):
     for p in (ROOT, os.path.join(ROOT, '3d-reconstruction-tool_b200'), os.path.join(ROOT, '3d-reconstruction-tool_b200', 'src')):
         sys.path.insert(0, p)
     import torch.distributed as dist
@@ -35,7 +35,7 @@ def _run(rank, ws, port, q):
     cam = Camera(K=sc.K.copy(), dist=np.zeros(5))
     poses = {i: CameraPose(R=sc.poses[i][0], t=sc.poses[i][1]) for i in sc.poses}
     pm = PatchMatchMVS(cam, scale=1.0, patch_size=7, num_iterations=2, num_samples=2, min_views=2, seed=5,
-                       device=f'cuda:{rank}')
+                       device=f'cuda:{rank}', consistency=mode, geo_min_views=1, geo_rel_thresh=0.02, geo_px_thresh=2.0)
     sparse = np.stack([np.zeros(20), np.zeros(20), np.linspace(4.0, 6.0, 20)], axis=1)
     p, c = pm.reconstruct(sc.images, poses, sparse_points=sparse)
     q.put((rank, p, c))
@@ -44,7 +44,9 @@ def _run(rank, ws, port, q):
 
 
 @pytest.mark.timeout(300)
-def test_two_rank_reconstruct_equals_single_rank():
+@pytest.mark.parametrize('mode', ['photometric', 'geometric'])
+def test_two_rank_reconstruct_equals_single_rank(mode):
+    """'geometric' additionally exercises the NCCL all-gather of the depth maps."""
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     ctx = mp.get_context('spawn')
@@ -52,7 +54,7 @@ def test_two_rank_reconstruct_equals_single_rank():
     for ws in (1, 2):
         q = ctx.Queue()
         port = _free_port()
-        procs = [ctx.Process(target=_run, args=(r, ws, port, q)) for r in range(ws)]
+        procs = [ctx.Process(target=_run, args=(r, ws, port, q, mode)) for r in range(ws)]
         for p in procs:
             p.start()
         res = dict((r, (p, c)) for r, p, c in [q.get(timeout=240) for _ in range(ws)])
