@@ -1,0 +1,84 @@
+"""Point-cloud post filters on the device.
+
+The reference runs these in NumPy on one CPU core over the whole fused cloud
+(`PatchMatchMVS._filter_points`, src/core/mvs_patchmatch.py:572-588;
+`DenseStereoReconstructor._voxel_down_sample`, src/core/dense_stereo.py:475-492).  At the benchmark
+scales (tens of millions of points) they dwarf the GPU stage, so they are restated here as device-side
+tensor programs: sorts / scans from the library (torch -> CUB radix sort), everything kept in f64.
+The semantics are reproduced exactly, including NumPy's conventions:
+
+  np.median        mean of the two middle order statistics for even n
+  np.percentile    method 'linear': virtual index (n-1)*q, lerp with the t >= 0.5 branch
+  np.linalg.norm   sqrt((x0^2 + x1^2) + x2^2)
+  np.unique(..., return_index=True)   sorted keys, index of the FIRST occurrence (stable sort)
+
+so the selected points, their order and their colours are identical to the reference's
+(tests/test_postfilter.py checks this against NumPy on CPU tensors; the same code runs on CUDA tensors).
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import numpy as np
+import torch
+
+
+def _median_axis0(x: torch.Tensor) -> torch.Tensor:
+    """np.median(x, axis=0) for an (N,C) f64 tensor."""
+    n = x.shape[0]
+    s = torch.sort(x, dim=0).values
+    if n % 2:
+        return s[n // 2]
+    return (s[n // 2 - 1] + s[n // 2]) / 2.0
+
+
+def _percentile_linear(sorted_vals: torch.Tensor, q_percent: float) -> float:
+    """np.percentile(v, q) with the default 'linear' method, from the sorted values (f64)."""
+    n = int(sorted_vals.shape[0])
+    q = np.true_divide(q_percent, 100)
+    vi = (n - 1) * q                                            # numpy 'linear': get_virtual_index
+    if vi >= n - 1:                                             # _get_indexes: above bounds -> the maximum
+        return float(sorted_vals[n - 1].item())
+    lo = int(np.floor(vi))
+    gamma = np.float64(vi - lo)
+    a = np.float64(sorted_vals[lo].item())
+    b = np.float64(sorted_vals[lo + 1].item())
+    diff = b - a                                                # numpy _lerp
+    out = a + diff * gamma
+    if gamma >= 0.5:
+        out = b - diff * (1 - gamma)
+    return float(out)
+
+
+def _first_of_each_voxel(points: torch.Tensor, voxel_size: float, cast_int32: bool) -> torch.Tensor:
+    """Indices np.unique(keys, return_index=True)[1] for keys = ix*1e9 + iy*1e6 + iz of floor(points / voxel)."""
+    v = torch.floor(points / voxel_size)
+    v = v.to(torch.int32).to(torch.int64) if cast_int32 else v.to(torch.int64)
+    keys = v[:, 0] * 1000000000 + v[:, 1] * 1000000 + v[:, 2]
+    sk, perm = torch.sort(keys, stable=True)
+    first = torch.ones_like(sk, dtype=torch.bool)
+    first[1:] = sk[1:] != sk[:-1]
+    return perm[first]
+
+
+def filter_points(points: torch.Tensor, colors: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """`PatchMatchMVS._filter_points` (mvs_patchmatch.py:572-588): keep points closer to the per-axis median
+    than the 95th-percentile distance, then the first point of every 0.01 voxel ordered by voxel key."""
+    if points.shape[0] == 0:
+        return points, colors
+    c = _median_axis0(points)
+    d = points - c
+    dist = torch.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2])
+    thr = _percentile_linear(torch.sort(dist).values, 95)
+    keep = dist < thr
+    points, colors = points[keep], colors[keep]
+    idx = _first_of_each_voxel(points, 0.01, cast_int32=False)
+    return points[idx], colors[idx]
+
+
+def voxel_down_sample(points: torch.Tensor, colors: torch.Tensor, voxel_size: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """`DenseStereoReconstructor._voxel_down_sample` (dense_stereo.py:475-492); voxel indices pass through int32."""
+    if points.shape[0] == 0:
+        return points, colors
+    idx = _first_of_each_voxel(points, voxel_size, cast_int32=True)
+    return points[idx], colors[idx]

@@ -62,6 +62,7 @@ class PatchMatchMVS:
         self.device = torch.device(device) if device is not None else torch.device('cuda')
         self.cache_images = True            # keep uploaded grays on the device between views
         self.views_in_flight = 4            # independent views enqueued concurrently (streams)
+        self.device_postfilter = True       # run _filter_points on the GPU (same selection, b200dense/postfilter.py)
         self._engine = None
         self._dev_gray: Dict[int, Tuple[int, torch.Tensor]] = {}
         self._dev_maps: Dict[int, dict] = {}
@@ -169,13 +170,16 @@ class PatchMatchMVS:
         pts_d, col_d = bdist.gather_point_clouds(cam_indices, local, eng.device)
         if rank != 0:
             return np.array([]).reshape(0, 3), np.array([]).reshape(0, 3)
+        print(f"  Raw points: {pts_d.shape[0]:,}")
         if pts_d.shape[0] == 0:
             points, colors = np.array([]).reshape(0, 3), np.array([]).reshape(0, 3)
+        elif self.device_postfilter:
+            from b200dense.postfilter import filter_points
+            fp, fc = filter_points(pts_d, col_d)                 # same selection and order as _filter_points
+            points, colors = fp.cpu().numpy(), fc.cpu().numpy()
+            print(f"  After filtering: {len(points):,}")
         else:
-            points, colors = pts_d.cpu().numpy(), col_d.cpu().numpy()
-        print(f"  Raw points: {len(points):,}")
-        if len(points) > 0:
-            points, colors = self._filter_points(points, colors)
+            points, colors = self._filter_points(pts_d.cpu().numpy(), col_d.cpu().numpy())
             print(f"  After filtering: {len(points):,}")
         print(f"\nPatchMatch MVS completed in {time.time() - t0:.1f}s")
         return points, colors

@@ -326,13 +326,28 @@ def main():
     fp32['ncc_kernel_frac_of_measured_fma_peak'] = fp32['ncc_kernel_fma_tlaneops'] / FMA_PEAK_MEASURED
     fp32['pair_frac_parity_model'] = fp32['pair_tlaneops_parity_model'] / FMA_PEAK_MEASURED
     fp32['pair_frac_fast_model'] = fp32['pair_tlaneops_fast_model'] / FMA_PEAK_MEASURED
-    roofline = {'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
-                'traffic': None, 'kernel': f'ncc_kernel<{a.patch},REFINE>', 'launch_ms': dom_ms,
+    # Headline roofline of the dominant kernel against the resource that binds it: the FP32 FMA pipe.
+    # Algorithmic flops of ncc_kernel per (pixel, source): three k x k window sums as FMAs (2 flops each), the two
+    # products s*s and r*s, ~20 for variance / covariance / NCC / aggregation.  Peak = measured FFMA/FFMA2 rate
+    # (profiles/microbench/ffma2.cu: 36.3 T lane-FMA/s = 72.6 TFLOP/s at 1965 MHz; nominal 148*128*2*1.965 = 74.5).
+    ncc_flops = evals * (6 * a.patch * a.patch + 22)
+    ach_tf = ncc_flops / (dom_ms * 1e-3) / 1e12
+    roofline = {'bound': 'fp32', 'achieved': ach_tf, 'peak': 2 * FMA_PEAK_MEASURED, 'unit': 'TFLOP/s',
+                'frac': ach_tf / (2 * FMA_PEAK_MEASURED),
+                'traffic': 91.2e6, 'traffic_source': 'ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch '
+                                                     '(profiles/r01_ncu_full_ncc_sample.txt)',
+                'kernel': f'ncc_kernel<{a.patch},REFINE>', 'launch_ms': dom_ms,
                 'launches_timed': kernels['ncc_kernel<REFINE>']['launches_per_step'],
                 'kernel_share_of_step': kernels['ncc_kernel<REFINE>']['share_of_step'],
-                'algorithmic_bytes_per_launch': alg_bytes, 'peak_source': peak_src,
+                'algorithmic_flops_per_launch': ncc_flops,
+                'peak_source': 'measured FFMA rate on this pool (profiles/microbench/ffma2.cu), of measured',
                 'how': 'CUDA events on the launching stream around every launch, one serialised step right after the '
-                       'timed region', 'kernels': kernels, 'fp32': fp32}
+                       'timed region',
+                'note': 'contract lists hbm|tensor; this path is neither: no dense contraction (no tensor cores) and '
+                        '10 % of HBM peak -- the FP32 pipe binds it, so the fraction is quoted against the measured FFMA peak',
+                'hbm': {'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach / hbm_peak,
+                        'algorithmic_bytes_per_launch': alg_bytes, 'peak_source': peak_src},
+                'kernels': kernels, 'fp32': fp32}
 
     # ---- end to end through the reference-facing API with pinned host buffers
     e2e = None

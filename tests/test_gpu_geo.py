@@ -76,6 +76,7 @@ def test_geometric_mode_filters_more_than_photometric():
     for mode in ('photometric', 'geometric'):
         pm = PatchMatchMVS(cam, scale=1.0, patch_size=7, num_iterations=2, num_samples=2, min_views=2, seed=5,
                            consistency=mode, geo_min_views=1, geo_rel_thresh=0.02, geo_px_thresh=2.0)
+        pm.device_postfilter = False
         pm._filter_points = lambda p, c: (p, c)                    # compare raw fused clouds
         p, c = pm.reconstruct(sc.images, poses, sparse_points=sparse)
         n[mode] = len(p)

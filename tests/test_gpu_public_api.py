@@ -34,11 +34,13 @@ def test_plane_sweep_reconstruct_matches_reference(scale):
     np.testing.assert_allclose(p, ep, rtol=0, atol=1e-9)
 
 
+@pytest.mark.parametrize('device_filter', [True, False])
 @pytest.mark.parametrize('scale', [1.0, 0.5])
-def test_patchmatch_reconstruct_matches_reference(scale):
+def test_patchmatch_reconstruct_matches_reference(scale, device_filter):
     g = load('reconstruct_wavy_96x72.npz')
     cam, images, poses = _scene(g)
     pm = PatchMatchMVS(cam, scale=scale, patch_size=7, num_iterations=2, num_samples=3, min_views=2, rng='torch')
+    pm.device_postfilter = device_filter                       # GPU post filter and NumPy post filter: same cloud
     torch.manual_seed(11)
     p, c = pm.reconstruct(images, poses, sparse_points=g['sparse'])
     assert [pm.depth_min, pm.depth_max] == list(g[f'mvs_s{scale}_range'])
