@@ -484,6 +484,24 @@ int b200d_geo_consistency(const float *d_depth_ref, const float *const *d_depth_
     return cuda_check(cudaGetLastError(), "geo_consistency_kernel launch");
 }
 
+// Host-side: ASCII PLY in the reference's exact format (src/core/utils.py:8-37): "%.6f %.6f %.6f %d %d %d\n".
+// The reference formats one point per Python iteration; this is a buffered C writer (same bytes).
+int b200d_write_ply_ascii(const char *path, const double *points, const uint8_t *colors, int64_t n) {
+    if (!path || n < 0 || (n > 0 && (!points || !colors))) return fail(B200D_ERR_ARG, "bad argument");
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(B200D_ERR_ARG, "cannot open output file");
+    std::vector<char> buf(1 << 22);
+    setvbuf(f, buf.data(), _IOFBF, buf.size());
+    fprintf(f, "ply\nformat ascii 1.0\nelement vertex %lld\nproperty float x\nproperty float y\nproperty float z\n"
+               "property uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n", (long long)n);
+    for (int64_t i = 0; i < n; ++i)
+        fprintf(f, "%.6f %.6f %.6f %d %d %d\n", points[3 * i], points[3 * i + 1], points[3 * i + 2], (int)colors[3 * i],
+                (int)colors[3 * i + 1], (int)colors[3 * i + 2]);
+    const bool bad = ferror(f) != 0;
+    if (fclose(f) != 0 || bad) return fail(B200D_ERR_ARG, "write failed");
+    return B200D_OK;
+}
+
 int b200d_mask_backproject(const float *d_depth, const float *d_conf, const uint8_t *d_bgr, int H, int W,
                            const double *Kinv64, const double *R64, const double *t64, float min_conf, int mode,
                            double *d_points, uint8_t *d_colors, int64_t *d_count, void *d_scratch, void *stream) {

@@ -1,6 +1,7 @@
 """Point-cloud output in the reference's format (reference: src/core/utils.py:8-87):
 ASCII PLY, `x y z` as %.6f floats and `red green blue` as uchar, one vertex per line.
-The writer is vectorised (the reference formats one point per Python iteration)."""
+The vertex lines are written by a buffered C routine of the dense library (b200d_write_ply_ascii, same bytes as
+the reference's per-point Python loop); if the library has not been built a pure-Python writer is used."""
 from pathlib import Path
 
 import numpy as np
@@ -9,10 +10,29 @@ _HEADER = ("ply\nformat ascii 1.0\nelement vertex {n}\nproperty float x\npropert
            "property uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n")
 
 
+def _native_writer():
+    try:
+        from b200dense import _cabi
+        return _cabi.load().b200d_write_ply_ascii
+    except Exception:                       # library not built / not importable: formatting is host-only work
+        return None
+
+
 def save_ply(points: np.ndarray, colors: np.ndarray, output_path: str):
     out = Path(output_path)
     out.parent.mkdir(parents=True, exist_ok=True)
     n = len(points)
+    native = _native_writer()
+    if native is not None:
+        import ctypes as C
+        xyz = np.ascontiguousarray(np.asarray(points, dtype=np.float64).reshape(n, 3))
+        rgb = np.ascontiguousarray(np.asarray(colors).reshape(n, 3).astype(int).astype(np.uint8))
+        rc = native(str(out).encode(), xyz.ctypes.data_as(C.POINTER(C.c_double)),
+                    rgb.ctypes.data_as(C.POINTER(C.c_uint8)), n)
+        if rc != 0:
+            raise OSError(f"could not write {out}")
+        print(f"Saved {n:,} points to {out}")
+        return
     with open(out, 'w') as f:
         f.write(_HEADER.format(n=n))
         if n:

@@ -146,6 +146,10 @@ B200D_API int b200d_mask_backproject(const float *d_depth, const float *d_conf, 
                            float min_conf, int mode, double *d_points, uint8_t *d_colors,
                            int64_t *d_count, void *d_scratch, void *stream);
 
+/* HOST function (no CUDA): replaces the per-point Python loop of save_ply (src/core/utils.py:8-37).  Writes the
+ * same bytes: ASCII PLY header, then "%.6f %.6f %.6f %d %d %d" per vertex.  points (n,3) f64, colors (n,3) u8 RGB. */
+B200D_API int b200d_write_ply_ascii(const char *path, const double *points, const uint8_t *colors, int64_t n);
+
 /* EXTENSION (no counterpart in the reference, whose consistency check is photometric -- SURVEY F6): cross-view
  * geometric consistency.  For every reference pixel: back-project at d_depth_ref, project into each source,
  * read that source's depth map at the nearest pixel, back-project, return to the reference camera; a source is

@@ -128,3 +128,26 @@ def test_depthnormalmap_fields():
     z = np.zeros((2, 2))
     dm = DepthNormalMap(depth=z, normal=np.zeros((2, 2, 3)), confidence=z)
     assert dm.depth is z and dm.normal.shape == (2, 2, 3)
+
+
+def test_native_ply_writer_bytes_equal_reference_format(tmp_path):
+    """b200d_write_ply_ascii writes byte-for-byte what the reference's per-point Python loop writes
+    (utils.py:20-35), including negative zero, large and tiny magnitudes."""
+    import time
+    rng = np.random.default_rng(0)
+    pts = np.concatenate([rng.normal(size=(20000, 3)) * 10, np.array([[-0.0, 1e-9, -1e-7], [123456.7891234, -5e5, 0.5]])])
+    col = rng.integers(0, 256, size=(len(pts), 3)).astype(np.uint8)
+    out = tmp_path / 'n.ply'
+    t0 = time.perf_counter()
+    save_ply(pts, col, str(out))
+    t_native = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    lines = ["ply", "format ascii 1.0", f"element vertex {len(pts)}", "property float x", "property float y",
+             "property float z", "property uchar red", "property uchar green", "property uchar blue", "end_header"]
+    for i in range(len(pts)):                                     # the reference's loop
+        x, y, z = pts[i]
+        r, g, b = col[i].astype(int)
+        lines.append(f"{x:.6f} {y:.6f} {z:.6f} {r} {g} {b}")
+    t_ref = time.perf_counter() - t0
+    assert out.read_text() == "\n".join(lines) + "\n"
+    assert t_native < t_ref
