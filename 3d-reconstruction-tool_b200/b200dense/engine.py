@@ -94,6 +94,7 @@ class DenseEngine:
         torch.cuda.set_device(self.device)
         self._scratch: Dict[Tuple[str, int, int, int], torch.Tensor] = {}
         self._streams: List[torch.cuda.Stream] = []
+        self._tables: Dict[tuple, tuple] = {}
         self.launches = 0                     # kernels of ours enqueued (bench's gpu_launches claim)
 
     # ------------------------------------------------------------------ helpers
@@ -242,6 +243,24 @@ class DenseEngine:
                                                    float(px_thresh), float(rel_thresh), _ptr(out), self._stream()))
         self.launches += 1
         return out
+
+    def prepare_image(self, bgr: torch.Tensor, nh: int, nw: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Device `_prepare_images` of one BGR u8 image (H,W,3): -> (colour (nh,nw,3) u8, gray (nh,nw) f32),
+        bit-identical to cv.resize + cv.cvtColor + /255 (mvs_patchmatch.py:176-177)."""
+        from .prepare import resize_tables
+        H, W = int(bgr.shape[0]), int(bgr.shape[1])
+        key = ('prep', H, W, nh, nw)
+        tabs = self._tables.get(key)
+        if tabs is None:
+            xi, xa, yi, ya = resize_tables(H, W, nh, nw)
+            tabs = tuple(torch.from_numpy(np.ascontiguousarray(t)).to(self.device) for t in (xi, xa, yi, ya))
+            self._tables[key] = tabs
+        color = torch.empty((nh, nw, 3), dtype=torch.uint8, device=self.device)
+        gray = torch.empty((nh, nw), dtype=torch.float32, device=self.device)
+        _cabi.check(self.lib.b200d_prepare_image(_ptr(bgr), H, W, nh, nw, _ptr(tabs[0]), _ptr(tabs[1]), _ptr(tabs[2]),
+                                                 _ptr(tabs[3]), _ptr(color), _ptr(gray), self._stream()))
+        self.launches += 1
+        return color, gray
 
     def mask_backproject(self, depth: torch.Tensor, conf: torch.Tensor, bgr: torch.Tensor, Kinv64: np.ndarray,
                          R: np.ndarray, t: np.ndarray, min_conf: float, mode: int,

@@ -15,6 +15,7 @@
 #include "fuse_kernels.cuh"
 #include "geo_kernels.cuh"
 #include "ncc_kernels.cuh"
+#include "prep_kernels.cuh"
 #include "sample_kernels.cuh"
 
 using namespace b200d;
@@ -482,6 +483,19 @@ int b200d_geo_consistency(const float *d_depth_ref, const float *const *d_depth_
     ProfScope prof(5000, st);
     geo_consistency_kernel<<<dim3((W + 31) / 32, (H + 7) / 8, 1), dim3(32, 8, 1), 0, st>>>(a);
     return cuda_check(cudaGetLastError(), "geo_consistency_kernel launch");
+}
+
+int b200d_prepare_image(const uint8_t *d_bgr, int H, int W, int nh, int nw, const int32_t *d_xi, const int16_t *d_xa,
+                        const int32_t *d_yi, const int16_t *d_ya, uint8_t *d_color, float *d_gray, void *stream) {
+    if (H < 1 || W < 1 || nh < 1 || nw < 1) return fail(B200D_ERR_ARG, "empty image");
+    if (!d_bgr || !d_xi || !d_xa || !d_yi || !d_ya || !d_color || !d_gray) return fail(B200D_ERR_ARG, "null pointer");
+    PrepArgs a;
+    a.src = d_bgr; a.H = H; a.W = W; a.nh = nh; a.nw = nw; a.xi = d_xi; a.yi = d_yi; a.xa = d_xa; a.ya = d_ya;
+    a.color = d_color; a.gray = d_gray;
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(6000, st);
+    prepare_image_kernel<<<dim3((nw + 31) / 32, (nh + 7) / 8, 1), dim3(32, 8, 1), 0, st>>>(a);
+    return cuda_check(cudaGetLastError(), "prepare_image_kernel launch");
 }
 
 // Host-side: ASCII PLY in the reference's exact format (src/core/utils.py:8-37): "%.6f %.6f %.6f %d %d %d\n".

@@ -33,6 +33,7 @@ class DenseStereoReconstructor:
         self.device = torch.device(device) if device is not None else torch.device('cuda')
         self._engine = None
         self.views_in_flight = 2            # independent reference views enqueued concurrently (streams)
+        self.device_prepare = True          # run _prepare_images on the GPU (bit-identical to the OpenCV calls)
         self._dev_gray: Dict[int, Tuple[int, torch.Tensor]] = {}
         if torch.cuda.is_available():
             print(f"Dense stereo using GPU: {torch.cuda.get_device_name()}")
@@ -50,7 +51,31 @@ class DenseStereoReconstructor:
             self._engine = DenseEngine(self.device)
         return self._engine
 
+    def _prepare_images_device(self, images: List[dict], indices: List[int]) -> Dict:
+        """Device form of `_prepare_images`, filled lazily per view (bit-exact resize + gray kernel)."""
+        out = {}
+        for idx in indices:
+            h, w = images[idx]['image'].shape[:2]
+            out[idx] = {'image': images[idx]['image'], 'shape': (int(h * self.scale), int(w * self.scale))}
+        return out
+
+    def _ensure_device_image(self, entry: dict) -> None:
+        if 'gray_dev' not in entry:
+            eng = self.engine
+            nh, nw = entry['shape']
+            entry['color_dev'], entry['gray_dev'] = eng.prepare_image(eng.to_device(entry['image'], torch.uint8), nh, nw)
+
+    def _color_on_device(self, processed: Dict, idx: int) -> torch.Tensor:
+        entry = processed[idx]
+        if 'image' in entry and 'color' not in entry:
+            self._ensure_device_image(entry)
+            return entry['color_dev']
+        return self.engine.to_device(entry['color'], torch.uint8)
+
     def _gray_on_device(self, processed: Dict, idx: int) -> torch.Tensor:
+        if 'gray' not in processed[idx]:
+            self._ensure_device_image(processed[idx])
+            return processed[idx]['gray_dev']
         g = processed[idx]['gray']
         hit = self._dev_gray.get(idx)
         if hit is not None and hit[0] == id(g):
@@ -75,7 +100,8 @@ class DenseStereoReconstructor:
             return np.array([]), np.array([])
 
         print("\nPreparing images...")
-        processed = self._prepare_images(images, camera_indices)
+        processed = (self._prepare_images_device(images, camera_indices) if self.device_prepare
+                     else self._prepare_images(images, camera_indices))
         self._dev_gray.clear()
 
         depth_min, depth_max = self._depth_range(poses, camera_indices)
@@ -99,7 +125,7 @@ class DenseStereoReconstructor:
 
             def job(slot, ref_idx=ref_idx, neighbors=neighbors):
                 out = self._sweep_device(ref_idx, neighbors, processed, poses, depth_min, depth_max, slot=slot)
-                bgr = eng.to_device(processed[ref_idx]['color'], torch.uint8)
+                bgr = self._color_on_device(processed, ref_idx)
                 return eng.mask_backproject(out['depth_map'], out['confidence'], bgr, Kinv, poses[ref_idx].R,
                                             poses[ref_idx].t, float(self.min_views - 0.5), 1, sync=False, slot=slot)
             jobs.append(job)

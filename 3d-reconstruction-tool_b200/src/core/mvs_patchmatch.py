@@ -63,6 +63,7 @@ class PatchMatchMVS:
         self.cache_images = True            # keep uploaded grays on the device between views
         self.views_in_flight = 4            # independent views enqueued concurrently (streams)
         self.device_postfilter = True       # run _filter_points on the GPU (same selection, b200dense/postfilter.py)
+        self.device_prepare = True          # run _prepare_images on the GPU (bit-identical to the OpenCV calls)
         self._engine = None
         self._dev_gray: Dict[int, Tuple[int, torch.Tensor]] = {}
         self._dev_maps: Dict[int, dict] = {}
@@ -82,7 +83,32 @@ class PatchMatchMVS:
             self._engine = DenseEngine(self.device)
         return self._engine
 
+    def _prepare_images_device(self, images: List[dict], indices: List[int]) -> Dict:
+        """Device form of `_prepare_images`: entries are filled lazily (first use uploads the photograph as uint8 and
+        runs the bit-exact resize + gray kernel), so a rank only prepares the views it touches."""
+        out = {}
+        for idx in indices:
+            h, w = images[idx]['image'].shape[:2]
+            out[idx] = {'image': images[idx]['image'], 'shape': (int(h * self.scale), int(w * self.scale))}
+        return out
+
+    def _ensure_device_image(self, entry: dict) -> None:
+        if 'gray_dev' not in entry:
+            eng = self.engine
+            nh, nw = entry['shape']
+            entry['color_dev'], entry['gray_dev'] = eng.prepare_image(eng.to_device(entry['image'], torch.uint8), nh, nw)
+
+    def _color_on_device(self, images: Dict, idx: int) -> torch.Tensor:
+        entry = images[idx]
+        if 'image' in entry and 'color' not in entry:
+            self._ensure_device_image(entry)
+            return entry['color_dev']
+        return self.engine.to_device(entry['color'], torch.uint8)
+
     def _gray_on_device(self, images: Dict, idx: int) -> torch.Tensor:
+        if 'gray' not in images[idx]:
+            self._ensure_device_image(images[idx])
+            return images[idx]['gray_dev']
         g = images[idx]['gray']
         hit = self._dev_gray.get(idx)
         if self.cache_images and hit is not None and hit[0] == id(g):
@@ -117,7 +143,8 @@ class PatchMatchMVS:
         self._estimate_depth_range(poses, sparse_points)
         print(f"  Depth range: [{self.depth_min:.2f}, {self.depth_max:.2f}]")
         print("\nPreparing images...")
-        proc_images = self._prepare_images(images, cam_indices)
+        proc_images = (self._prepare_images_device(images, cam_indices) if self.device_prepare
+                       else self._prepare_images(images, cam_indices))
 
         print(f"\nComputing depth maps for {n_cams} views...")
         self._dev_gray.clear()
@@ -160,7 +187,7 @@ class PatchMatchMVS:
         local = {}
         for pos, ref_idx, _ in job_views:
             out = maps[ref_idx]
-            bgr = eng.to_device(proc_images[ref_idx]['color'], torch.uint8)
+            bgr = self._color_on_device(proc_images, ref_idx)
             pts, cols = eng.mask_backproject(out['depth'], out['confidence'], bgr, Kinv, poses[ref_idx].R,
                                              poses[ref_idx].t, float(self.min_views), 0)
             local[ref_idx] = (pts.clone(), cols.clone())

@@ -146,6 +146,15 @@ B200D_API int b200d_mask_backproject(const float *d_depth, const float *d_conf, 
                            float min_conf, int mode, double *d_points, uint8_t *d_colors,
                            int64_t *d_count, void *d_scratch, void *stream);
 
+/* Replaces `_prepare_images` (mvs_patchmatch.py:167-191, dense_stereo.py:156-176) for one image:
+ * cv.resize(INTER_LINEAR) of the BGR uint8 image to (nh,nw), BGR2GRAY, /255 -- OpenCV's fixed-point arithmetic,
+ * bit-exact.  d_xi/d_xa (nw / nw*2) and d_yi/d_ya (nh / nh*2) are the source-index and 11-bit coefficient tables
+ * OpenCV builds per output column / row (b200dense/prepare.py builds them).  Outputs: d_color (nh,nw,3) u8 BGR,
+ * d_gray (nh,nw) fp32 in [0,1]. */
+B200D_API int b200d_prepare_image(const uint8_t *d_bgr, int H, int W, int nh, int nw, const int32_t *d_xi,
+                                  const int16_t *d_xa, const int32_t *d_yi, const int16_t *d_ya, uint8_t *d_color,
+                                  float *d_gray, void *stream);
+
 /* HOST function (no CUDA): replaces the per-point Python loop of save_ply (src/core/utils.py:8-37).  Writes the
  * same bytes: ASCII PLY header, then "%.6f %.6f %.6f %d %d %d" per vertex.  points (n,3) f64, colors (n,3) u8 RGB. */
 B200D_API int b200d_write_ply_ascii(const char *path, const double *points, const uint8_t *colors, int64_t n);
