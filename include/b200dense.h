@@ -21,8 +21,9 @@
  * Arithmetic modes
  *   B200D_PARITY  IEEE-RN fp32 in the exact operation order of the reference's CPU path
  *                 (SURVEY.md §7.4): bit-identical to oracle/dense_oracle.c.
- *   B200D_FAST    same algorithm, re-associated for speed (composed reprojection, sliding
- *                 window sums); NCC agrees to ~1e-5, not bit-exact.
+ *   B200D_FAST    reserved.  A re-associated variant (composed reprojection, separable window sums) was built
+ *                 and measured: 1.6x faster but its NCC misses the 1e-4 tolerance wherever a patch is flat
+ *                 (DESIGN.md 5.8), so it is not shipped; passing it returns B200D_ERR_UNSUPPORTED.
  */
 #ifndef B200DENSE_H
 #define B200DENSE_H
