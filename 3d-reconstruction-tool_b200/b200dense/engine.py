@@ -244,6 +244,14 @@ class DenseEngine:
         self.launches += 1
         return out
 
+    def knn_mean_dist(self, points: torch.Tensor, k: int = 20) -> torch.Tensor:
+        """Mean distance of every point to its k-1 nearest other points, f64 (dense_stereo.py:456-460)."""
+        n = int(points.shape[0])
+        out = torch.empty(n, dtype=torch.float64, device=self.device)
+        _cabi.check(self.lib.b200d_knn_mean_dist(_ptr(points), n, int(k), _ptr(out), self._stream()))
+        self.launches += 1
+        return out
+
     def prepare_image(self, bgr: torch.Tensor, nh: int, nw: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """Device `_prepare_images` of one BGR u8 image (H,W,3): -> (colour (nh,nw,3) u8, gray (nh,nw) f32),
         bit-identical to cv.resize + cv.cvtColor + /255 (mvs_patchmatch.py:176-177)."""

@@ -82,3 +82,26 @@ def voxel_down_sample(points: torch.Tensor, colors: torch.Tensor, voxel_size: fl
         return points, colors
     idx = _first_of_each_voxel(points, voxel_size, cast_int32=True)
     return points[idx], colors[idx]
+
+
+def filter_outliers(points: torch.Tensor, colors: torch.Tensor, engine, k: int = 20,
+                    std_ratio: float = 2.0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """`DenseStereoReconstructor._filter_outliers` with scikit-learn present (dense_stereo.py:439-466): statistical
+    outlier removal on the mean distance to the k-1 nearest neighbours, threshold mean + std_ratio * std.
+    The k-NN query is the device kernel (b200d_knn_mean_dist, exact f64); threshold and mask are NumPy on the
+    downloaded vector (the reference's own reductions, 4 MB at the 500k cap).  Above 500k points the reference draws
+    an unseeded random subsample; so does this (same non-determinism, by design of the reference)."""
+    n = int(points.shape[0])
+    if n < k + 1:
+        return points, colors
+    if n > 500000:
+        indices = torch.from_numpy(np.random.choice(n, 500000, replace=False)).to(points.device)
+        sample = points[indices].contiguous()
+    else:
+        indices = None
+        sample = points.contiguous()
+    mean_dist = engine.knn_mean_dist(sample, k).cpu().numpy()
+    threshold = np.mean(mean_dist) + std_ratio * np.std(mean_dist)
+    inlier = torch.from_numpy(mean_dist < threshold).to(points.device)
+    sel = indices[inlier] if indices is not None else inlier
+    return points[sel], colors[sel]

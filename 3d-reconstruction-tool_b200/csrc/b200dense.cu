@@ -14,6 +14,7 @@
 #include "b200dense.h"
 #include "fuse_kernels.cuh"
 #include "geo_kernels.cuh"
+#include "knn_kernels.cuh"
 #include "ncc_kernels.cuh"
 #include "prep_kernels.cuh"
 #include "sample_kernels.cuh"
@@ -483,6 +484,17 @@ int b200d_geo_consistency(const float *d_depth_ref, const float *const *d_depth_
     ProfScope prof(5000, st);
     geo_consistency_kernel<<<dim3((W + 31) / 32, (H + 7) / 8, 1), dim3(32, 8, 1), 0, st>>>(a);
     return cuda_check(cudaGetLastError(), "geo_consistency_kernel launch");
+}
+
+int b200d_knn_mean_dist(const double *d_points, int64_t n, int k, double *d_mean_dist, void *stream) {
+    if (!d_points || !d_mean_dist) return fail(B200D_ERR_ARG, "null pointer");
+    if (n < 1) return fail(B200D_ERR_ARG, "no points");
+    if (k < 2 || k > KNN_KMAX || k > n) return fail(B200D_ERR_ARG, "k must be in 2..32 and <= n");
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(7000, st);
+    const int64_t per_block = (int64_t)KNN_NT * KNN_Q;
+    knn_mean_dist_kernel<<<(unsigned)((n + per_block - 1) / per_block), KNN_NT, 0, st>>>(d_points, n, k, d_mean_dist);
+    return cuda_check(cudaGetLastError(), "knn_mean_dist_kernel launch");
 }
 
 int b200d_prepare_image(const uint8_t *d_bgr, int H, int W, int nh, int nw, const int32_t *d_xi, const int16_t *d_xa,

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(HERE, 'libb200dense.so')
 SRCS = ['b200dense.cu']
-DEPS = SRCS + ['device_math.cuh', 'sample_kernels.cuh', 'ncc_kernels.cuh', 'fuse_kernels.cuh', 'geo_kernels.cuh', 'prep_kernels.cuh',
+DEPS = SRCS + ['device_math.cuh', 'sample_kernels.cuh', 'ncc_kernels.cuh', 'fuse_kernels.cuh', 'geo_kernels.cuh', 'prep_kernels.cuh', 'knn_kernels.cuh',
                os.path.join(ROOT, 'include', 'b200dense.h')]
 
 

@@ -34,6 +34,7 @@ class DenseStereoReconstructor:
         self._engine = None
         self.views_in_flight = 2            # independent reference views enqueued concurrently (streams)
         self.device_prepare = True          # run _prepare_images on the GPU (bit-identical to the OpenCV calls)
+        self.device_postfilter = True       # outlier + voxel filters on the GPU (same selection as sklearn / NumPy)
         self._dev_gray: Dict[int, Tuple[int, torch.Tensor]] = {}
         if torch.cuda.is_available():
             print(f"Dense stereo using GPU: {torch.cuda.get_device_name()}")
@@ -140,6 +141,16 @@ class DenseStereoReconstructor:
         pts_d, col_d = bdist.gather_point_clouds(ref_indices, local, eng.device)
         if rank != 0:
             return np.array([]), np.array([])
+        if self.device_postfilter and pts_d.shape[0]:
+            from b200dense.postfilter import filter_outliers, voxel_down_sample
+            print("\nMerging point clouds...")
+            print(f"  Raw points: {pts_d.shape[0]:,}")
+            fp, fc = filter_outliers(pts_d, col_d, eng)
+            print(f"  After outlier removal: {fp.shape[0]:,}")
+            fp, fc = voxel_down_sample(fp, fc, 0.02)
+            print(f"  After voxel downsample: {fp.shape[0]:,}")
+            print(f"\nDense stereo completed in {time.time() - t0:.1f}s")
+            return fp.cpu().numpy(), fc.cpu().numpy()
         all_points = [pts_d.cpu().numpy()] if pts_d.shape[0] else []
         all_colors = [col_d.cpu().numpy()] if pts_d.shape[0] else []
 

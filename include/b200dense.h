@@ -156,6 +156,11 @@ B200D_API int b200d_prepare_image(const uint8_t *d_bgr, int H, int W, int nh, in
                                   const int16_t *d_xa, const int32_t *d_yi, const int16_t *d_ya, uint8_t *d_color,
                                   float *d_gray, void *stream);
 
+/* Replaces the k-NN query of DenseStereoReconstructor._filter_outliers (dense_stereo.py:456-460):
+ * d_mean_dist[i] = mean of the distances from point i to its k-1 nearest other points (f64, the values and the
+ * summation order scikit-learn's KD-tree query + np.mean produce).  d_points (n,3) f64; 2 <= k <= 32, k <= n. */
+B200D_API int b200d_knn_mean_dist(const double *d_points, int64_t n, int k, double *d_mean_dist, void *stream);
+
 /* HOST function (no CUDA): replaces the per-point Python loop of save_ply (src/core/utils.py:8-37).  Writes the
  * same bytes: ASCII PLY header, then "%.6f %.6f %.6f %d %d %d" per vertex.  points (n,3) f64, colors (n,3) u8 RGB. */
 B200D_API int b200d_write_ply_ascii(const char *path, const double *points, const uint8_t *colors, int64_t n);
