@@ -457,6 +457,10 @@ int b200d_plane_sweep(const float *d_ref, const float *const *d_nbr, const b200d
     s.cand = nullptr;
     a.n_src = cams->n_src; a.H = H; a.W = W; a.mean1 = sc.mean1; a.var1 = sc.var1; a.valid = sc.valid;
     a.thresh = thresh; a.n_planes = D; a.depths = d_depths;
+    if (thresh > 1e-3f && thresh < 1e3f) {                    // quick comparison bounds (ncc_kernels.cuh, N_SWEEP)
+        a.t_lo = (float)((0.999 * thresh) * (0.999 * thresh));
+        a.t_hi = (float)((1.001 * thresh) * (1.001 * thresh));
+    }
     a.conf = d_conf; a.idx = d_idx; a.depth_map = d_depth_map; a.ncc = d_ncc;
     for (int d = 0; d < D; ++d) {
         s.plane_depth = depths_host[d];

@@ -53,6 +53,7 @@ struct NccArgs {
     uint32_t view_id, eval_id;
     // N_SWEEP
     float thresh;
+    float t_lo, t_hi;                        // (0.999 thresh)^2, (1.001 thresh)^2 ; 0 = always take the exact comparison
     int plane, n_planes;
     const float *depths;
     float *conf, *depth_map, *ncc;
@@ -273,12 +274,27 @@ __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_
                 const float cov = sub(ars[q][p], mul(m1v, m2));
                 const bool valid = (vb[q] >> (8 * p + s)) & 1u;
                 if (MODE == N_SWEEP) {
-                    const float ncc = div_(cov, __fsqrt_rn(add(mul(v1v, v2), 1e-8f)));   // dense_stereo.py:344-345
+                    // ncc = cov / sqrt(var1*var2 + 1e-8) (dense_stereo.py:344-345) is only ever compared with the
+                    // threshold (:303).  The comparison is decided without the square root and the division whenever
+                    // cov^2 is clearly off thresh^2 * x (0.1 % margins, four orders above the rounding errors involved);
+                    // only the sliver around the threshold (and zero / negative / non-finite x) takes the exact path.
+                    const float x = add(mul(v1v, v2), 1e-8f);
+                    bool over;
                     if (a.ncc) {
+                        const float ncc = div_(cov, __fsqrt_rn(x));
                         const int gx = x0 + tx * PX + p, gy = y0 + ty * QY + q;
                         if (gx < W && gy < H) a.ncc[(((size_t)a.plane * S + s) * H + gy) * W + gx] = ncc;
+                        over = ncc > a.thresh;
+                    } else if (!(cov > 0.0f) && a.t_lo > 0.0f) {
+                        over = false;                       // ncc <= 0, -inf or NaN; the threshold is positive
+                    } else {
+                        const float c2 = mul(cov, cov);
+                        const bool pos = (x > 0.0f) & (a.t_lo > 0.0f);
+                        if (pos && c2 < mul(x, a.t_lo)) over = false;
+                        else if (pos && c2 > mul(x, a.t_hi)) over = true;
+                        else over = div_(cov, __fsqrt_rn(x)) > a.thresh;
                     }
-                    if ((ncc > a.thresh) && valid) total[q][p] = add(total[q][p], 1.0f);      // :303-304
+                    if (over && valid) total[q][p] = add(total[q][p], 1.0f);                  // :303-304
                 } else {
                     const float ncc = div_(cov, add(__fsqrt_rn(mul(v1v, v2)), 1e-8f));   // mvs_patchmatch.py:410
                     const float cost = sub(1.0f, ncc);

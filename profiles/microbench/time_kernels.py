@@ -62,9 +62,10 @@ def run(libpath):
     torch.cuda.synchronize()
     ms2, tags2 = eng.profile_end()
     sw = e0.elapsed_time(e1)
-    print('   sweep per-plane: sample', float(ms2[tags2 == 2032].mean()), 'ncc', float(ms2[tags2 == 507].mean()))
-    print(f"{os.path.basename(libpath):40s} view {view_ms:7.3f} ms  ncc-refine {out.get(411, 0):.4f}  sample-refine {out.get(2020, 0):.4f}  ncc-shift {out.get(311, 0):.4f}  "
-          f"sample-shift {out.get(2010, 0):.4f}  stats {out.get(11, 0):.4f}   sweep(D=64) {sw:7.2f} ms = {Hs * Ws * 64 / sw / 1e6:.2f} Gpix*planes/s")
+    out2 = {int(t): (float(ms2[tags2 == t].mean()), int((tags2 == t).sum())) for t in np.unique(tags2)}
+    print(f"{os.path.basename(libpath):40s} view {view_ms:7.3f} ms   sweep(D=64) {sw:7.2f} ms = {Hs * Ws * 64 / sw / 1e6:.2f} Gpix*planes/s")
+    print('   pm tags (ms):', {t: round(v, 4) for t, v in out.items()})
+    print('   sweep tags (ms, n):', {t: (round(v, 4), c) for t, (v, c) in out2.items()})
 
 
 if __name__ == '__main__':

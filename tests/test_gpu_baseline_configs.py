@@ -40,6 +40,15 @@ def test_config0_plane_sweep_640x480_full_volume(engine):
     assert np.array_equal(r['confidence'].cpu().numpy(), o['confidence'])
     assert np.array_equal(r['depth_map'].cpu().numpy(), o['depth_map'])
     assert o['confidence'].max() >= 3                                      # the scene does produce consistent planes
+    for th in (0.8, 0.3, 0.95):                                            # production path: quick threshold decision
+        q = engine.plane_sweep(d(gray[ref]), [d(gray[i]) for i in nb], ecams, depths, 7, th)
+        if th == 0.8:
+            assert np.array_equal(q['best_idx'].cpu().numpy(), o['best_idx'])
+            assert np.array_equal(q['confidence'].cpu().numpy(), o['confidence'])
+        else:
+            e = engine.plane_sweep(d(gray[ref]), [d(gray[i]) for i in nb], ecams, depths, 7, th, dump_ncc=True)
+            assert np.array_equal(q['best_idx'].cpu().numpy(), e['best_idx'].cpu().numpy())
+            assert np.array_equal(q['confidence'].cpu().numpy(), e['confidence'].cpu().numpy())
 
 
 @pytest.mark.timeout(900)

@@ -53,6 +53,12 @@ def test_plane_sweep_vs_reference_and_oracle(engine, name):
                         dump_ncc=True)
     assert np.array_equal(ncc, o['ncc'])
     assert np.array_equal(idx, o['best_idx'])
+    # production path (no NCC dump): the threshold test is decided without sqrt/div away from the threshold
+    q = engine.plane_sweep(dev(engine, g['gray'][ref]), [dev(engine, g['gray'][i]) for i in nb],
+                           engine_cams(g, ref, nb), d32, k, th)
+    assert np.array_equal(q['best_idx'].cpu().numpy(), o['best_idx'])
+    assert np.array_equal(q['confidence'].cpu().numpy(), g['confidence'])
+    assert np.array_equal(q['depth_map'].cpu().numpy(), g['depth_map'])
     # fusion: mask, count, order, colours exact; coordinates to 1e-9
     pts, col = engine.mask_backproject(r['depth_map'], r['confidence'], dev(engine, g['bgr'][ref], torch.uint8),
                                        np.linalg.inv(g['K_scaled']), g['R'][ref], g['t'][ref],
