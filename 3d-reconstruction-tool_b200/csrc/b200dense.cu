@@ -192,8 +192,13 @@ int launch_ncc_k(int patch, const NccArgs &a, cudaStream_t st) {
 template <int CAND, int BOUNDS>
 int launch_sample(const SampleArgs &a, cudaStream_t st) {
     ProfScope prof(2000 + CAND * 10 + BOUNDS, st);
-    const dim3 grid((a.W + SBX - 1) / SBX, (a.H + SBY - 1) / SBY, 1);
-    sample_kernel<CAND, BOUNDS><<<grid, dim3(SBX, SBY, 1), 0, st>>>(a);
+    const dim3 grid((a.W + SBX - 1) / SBX, (a.H + SBY - 1) / SBY, 1), block(SBX, SBY, 1);
+    switch (a.cams.n_src) {                  // the usual source counts get a fully unrolled kernel
+        case 4: sample_kernel<CAND, BOUNDS, 4><<<grid, block, 0, st>>>(a); break;
+        case 5: sample_kernel<CAND, BOUNDS, 5><<<grid, block, 0, st>>>(a); break;
+        case 6: sample_kernel<CAND, BOUNDS, 6><<<grid, block, 0, st>>>(a); break;
+        default: sample_kernel<CAND, BOUNDS, 0><<<grid, block, 0, st>>>(a); break;
+    }
     return cuda_check(cudaGetLastError(), "sample_kernel launch");
 }
 

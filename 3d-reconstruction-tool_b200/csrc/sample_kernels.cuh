@@ -42,7 +42,10 @@ struct SampleArgs {
 
 constexpr int SBX = 32, SBY = 8;         // thread block: 32 x 8 pixels
 
-template <int CAND, int BOUNDS>
+// NS > 0: number of sources known at compile time -- the loop is fully unrolled and every camera constant becomes a
+// constant-bank operand of the arithmetic instruction that uses it (no uniform loads, no index arithmetic);
+// NS == 0: run-time count.
+template <int CAND, int BOUNDS, int NS>
 __global__ void __launch_bounds__(SBX *SBY) sample_kernel(const __grid_constant__ SampleArgs a) {
     const int x = blockIdx.x * SBX + threadIdx.x, y = blockIdx.y * SBY + threadIdx.y;
     if (x >= a.W || y >= a.H) return;
@@ -83,9 +86,7 @@ __global__ void __launch_bounds__(SBX *SBY) sample_kernel(const __grid_constant_
 
     unsigned vmask = 0;
     float *out = a.smap + (size_t)y * a.Wp + x + a.pad;
-    const int S = a.cams.n_src;
-#pragma unroll 2
-    for (int s = 0; s < S; ++s) {
+    auto one_source = [&](int s) {
         float u, v, z, smp;
         if (!project_sample_fast(a.cams, s, pw, a.src[s], W, wm1, hm1, rw, rh, u, v, z, smp)) {
             float uv[2];
@@ -97,6 +98,14 @@ __global__ void __launch_bounds__(SBX *SBY) sample_kernel(const __grid_constant_
         if (BOUNDS != B_DEPTH) ok = ok & (u >= lo) & (u < hix) & (v >= lo) & (v < hiy);
         vmask |= (unsigned)ok << s;
         out[(size_t)s * a.map_stride] = smp;
+    };
+    if (NS > 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) one_source(s);
+    } else {
+        const int S = a.cams.n_src;
+#pragma unroll 2
+        for (int s = 0; s < S; ++s) one_source(s);
     }
     if (a.cand) a.cand[g] = cd;
     a.valid[g] = (uint8_t)vmask;
