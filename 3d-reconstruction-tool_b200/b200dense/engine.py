@@ -125,6 +125,12 @@ class DenseEngine:
         torch.cuda.current_stream().synchronize()
         return [PINNED.as_numpy(h) for h in hs]
 
+    def copy_stream(self) -> torch.cuda.Stream:
+        """Side stream for host->device uploads that should overlap the compute streams."""
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        return self._copy_stream
+
     # ------------------------------------------------------------------ concurrent views
     def run_views(self, jobs: Sequence, n_streams: int = 4) -> list:
         """Run independent per-view jobs concurrently on `n_streams` side streams.

@@ -322,11 +322,24 @@ class PatchMatchMVS:
         if not keep:
             self._dev_gray.clear()                       # re-upload: the caller asked for no caching across calls
         try:
-            for i in sorted({i for r, src in plan for i in [r] + src}):
-                self._gray_on_device(images, i)
+            # uploads go to a copy stream in order of first use; a view waits only for its own images, so the first
+            # views start while the later views' images are still crossing PCIe
+            ready = {}
+            copy_stream = eng.copy_stream()
+            copy_stream.wait_stream(torch.cuda.current_stream(eng.device))
+            with torch.cuda.stream(copy_stream):
+                for r, src in plan:
+                    for i in [r] + src:
+                        if i not in ready:
+                            self._gray_on_device(images, i)
+                            ready[i] = torch.cuda.Event()
+                            ready[i].record(copy_stream)
             jobs = []
             for r, src in plan:
                 def job(slot, r=r, src=src):
+                    st = torch.cuda.current_stream(eng.device)
+                    for i in [r] + src:
+                        st.wait_event(ready[i])
                     out = self._patchmatch_device(r, src, images, poses, slot=slot)
                     host = []
                     for k in ('depth', 'normal', 'confidence'):
