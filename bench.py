@@ -334,7 +334,7 @@ def main():
     ach_tf = ncc_flops / (dom_ms * 1e-3) / 1e12
     roofline = {'bound': 'fp32', 'achieved': ach_tf, 'peak': 2 * FMA_PEAK_MEASURED, 'unit': 'TFLOP/s',
                 'frac': ach_tf / (2 * FMA_PEAK_MEASURED),
-                'traffic': 88.4e6, 'traffic_source': 'ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch '
+                'traffic': 97.2e6, 'traffic_source': 'ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch '
                                                      '(profiles/r01_ncu_full_ncc_sample.txt)',
                 'kernel': f'ncc_kernel<{a.patch},REFINE>', 'launch_ms': dom_ms,
                 'launches_timed': kernels['ncc_kernel<REFINE>']['launches_per_step'],
