@@ -179,3 +179,44 @@ def test_exact_division_fallback_paths(engine):
         got = engine.pm_cost(dev(engine, gray[0]), [dev(engine, gray[i]) for i in src], ecams, dev(engine, depth), k, mode)
         exp = orc.pm_cost(gray[0], [gray[i] for i in src], ocams, depth, k, mode)
         assert np.array_equal(got.cpu().numpy(), exp, equal_nan=True), f'mode {mode}'
+
+
+@pytest.mark.parametrize('n_src', [1, 2, 3, 6, 7, 8])
+def test_every_source_count_bitexact(engine, n_src):
+    """sample_kernel has compile-time-unrolled variants for 4/5/6 sources and a run-time loop for the rest; the NCC
+    kernel double-buffers its TMA stages over any count up to B200D_MAX_SRC.  Cost, confidence, a PatchMatch view and a
+    plane sweep against the oracle for the counts the fixtures do not cover."""
+    from b200dense.engine import kinv32, make_cams
+    from b200dense.scenes import gray_f32, make_scene
+    sc = make_scene('wavy', 9, 96, 72, seed=11 + n_src, arc_deg=4.0)
+    gray = gray_f32(sc)
+    ref, src = 4, [3, 5, 2, 6, 1, 7, 0, 8][:n_src]
+    Ki = kinv32(sc.K)
+    R = [sc.poses[i][0] for i in range(9)]
+    t = [sc.poses[i][1] for i in range(9)]
+    ecams = make_cams(sc.K, Ki, R[ref], t[ref], [R[i] for i in src], [t[i] for i in src])
+    ocams = orc.Cams(sc.K, Ki, R[ref], t[ref], [R[i] for i in src], [t[i] for i in src])
+    H, W = gray[0].shape
+    dmin, dmax = sc.depth_range
+    g = np.random.default_rng(n_src)
+    depth = (g.random((H, W), dtype=np.float32) * np.float32(dmax - dmin) + np.float32(dmin))
+    d_ref, d_src = dev(engine, gray[ref]), [dev(engine, gray[i]) for i in src]
+    for mode in (0, 1):
+        a = engine.pm_cost(d_ref, d_src, ecams, dev(engine, depth), 7, mode).cpu().numpy()
+        b = orc.pm_cost(gray[ref], [gray[i] for i in src], ocams, depth, 7, mode)
+        assert np.array_equal(a, b, equal_nan=True)
+    iters, samples = 2, 2
+    n0 = g.standard_normal((H, W, 3), dtype=np.float32)
+    n0 /= np.linalg.norm(n0, axis=-1, keepdims=True)
+    ru = g.random((iters * samples, H, W), dtype=np.float32)
+    rn = g.standard_normal((iters * samples, H, W, 3), dtype=np.float32)
+    out = engine.pm_view(d_ref, d_src, ecams, 7, iters, samples, dmin, dmax, init_depth=dev(engine, depth),
+                         init_normal=dev(engine, n0), rand_u=dev(engine, ru), rand_n=dev(engine, rn))
+    exp = orc.pm_view(gray[ref], [gray[i] for i in src], ocams, 7, iters, samples, dmin, dmax, depth, n0, ru, rn)
+    for key in ('depth', 'normal', 'confidence'):
+        assert np.array_equal(out[key].cpu().numpy(), exp[key], equal_nan=True), key
+    depths = (1.0 / np.linspace(1 / dmax, 1 / dmin, 12)).astype(np.float32)
+    sw = engine.plane_sweep(d_ref, d_src, ecams, depths, 5, 0.8)
+    ex = orc.plane_sweep(gray[ref], [gray[i] for i in src], ocams, depths, 5, 0.8)
+    assert np.array_equal(sw['best_idx'].cpu().numpy(), ex['best_idx'])
+    assert np.array_equal(sw['confidence'].cpu().numpy(), ex['confidence'])
