@@ -102,3 +102,66 @@ def test_config3_shape_properties_1600x1200(engine):
     conf2 = engine.pm_cost(dg[ref], [dg[i] for i in src], ecams, runs[0]['depth'], 11, mode=1)
     assert np.array_equal(conf2.cpu().numpy(), a['confidence'])
     assert set(np.unique(a['confidence'])) <= {0.0, 1.0, 2.0, 3.0, 4.0, 5.0}
+
+
+@pytest.mark.timeout(900)
+def test_config2_shape_plane_sweep_1920x1080_n6(engine):
+    """BASELINE configs[2] shape (1920x1080, 6 neighbours, 7x7 NCC): 8 of the 256 planes bit-exact against the oracle,
+    then the full 256-plane sweep through properties (the running arg-max only ever improves; every plane subset
+    agrees with the full sweep wherever its own best plane wins)."""
+    sc = make_scene('turntable', 64, 1920, 1080, arc_deg=360.0 / 64, seed=0, device='cuda', render=[0, 1, 2, 3, 4, 5, 6])
+    gray = gray_f32(sc)
+    ref, nb = 3, [2, 4, 1, 5, 0, 6]
+    ecams, ocams = _cams(sc, ref, nb)
+    dmin, dmax = sc.depth_range
+    full = (1.0 / np.linspace(1 / dmax, 1 / dmin, 256)).astype(np.float32)
+    d = engine.to_device
+    dg = {i: d(gray[i]) for i in [ref] + nb}
+    sub = np.ascontiguousarray(full[::32])
+    r = engine.plane_sweep(dg[ref], [dg[i] for i in nb], ecams, sub, 7, 0.8)
+    o = orc.plane_sweep(gray[ref], [gray[i] for i in nb], ocams, sub, 7, 0.8)
+    assert np.array_equal(r['best_idx'].cpu().numpy(), o['best_idx'])
+    assert np.array_equal(r['confidence'].cpu().numpy(), o['confidence'])
+    assert np.array_equal(r['depth_map'].cpu().numpy(), o['depth_map'])
+    f = engine.plane_sweep(dg[ref], [dg[i] for i in nb], ecams, full, 7, 0.8)
+    fc, fi = f['confidence'].cpu().numpy(), f['best_idx'].cpu().numpy()
+    assert set(np.unique(fc)) <= {0.0, 1.0, 2.0, 3.0, 4.0, 5.0, 6.0}
+    assert np.all(fc >= o['confidence'])                                   # a superset of planes cannot lower the max
+    assert np.array_equal(f['depth_map'].cpu().numpy(), full[fi])
+    same = fc == o['confidence']                                            # first-max tie-break: the full sweep's winner
+    assert np.all(fi[same] <= 32 * o['best_idx'][same])                    # is never later than the subset's
+    assert fc.max() >= 3
+
+
+@pytest.mark.timeout(900)
+def test_config4_shape_patchmatch_3840x2160(engine):
+    """BASELINE configs[4] shape: one 3840x2160 view, 5 sources, 11x11 NCC; a short schedule (1 iteration, 1 sample:
+    two shifts, one refinement, confidence) bit-exact against the oracle, then mask + back-projection."""
+    sc = make_scene('turntable', 200, 3840, 2160, arc_deg=360.0 / 200, seed=0, device='cuda',
+                    render=[0, 8, 10, 12, 188, 190, 192])
+    gray = gray_f32(sc)
+    ref, src = 0, [190, 10, 188, 12, 8]
+    ecams, ocams = _cams(sc, ref, src)
+    H, W = 2160, 3840
+    dmin, dmax = sc.depth_range
+    g = np.random.default_rng(4)
+    depth0 = np.exp(g.random((H, W), dtype=np.float32) * np.float32(np.log(dmax / dmin)) + np.float32(np.log(dmin)))
+    n0 = g.standard_normal((H, W, 3), dtype=np.float32) * np.float32(0.3)
+    n0[..., 2] = -1
+    n0 /= np.linalg.norm(n0, axis=-1, keepdims=True)
+    ru = g.random((1, H, W), dtype=np.float32)
+    rn = g.standard_normal((1, H, W, 3), dtype=np.float32)
+    d = engine.to_device
+    r = engine.pm_view(d(gray[ref]), [d(gray[i]) for i in src], ecams, 11, 1, 1, dmin, dmax,
+                       init_depth=d(depth0), init_normal=d(n0), rand_u=d(ru), rand_n=d(rn))
+    o = orc.pm_view(gray[ref], [gray[i] for i in src], ocams, 11, 1, 1, dmin, dmax, depth0, n0, ru, rn)
+    assert np.array_equal(r['depth'].cpu().numpy(), o['depth'])
+    assert np.array_equal(r['normal'].cpu().numpy(), o['normal'])
+    assert np.array_equal(r['confidence'].cpu().numpy(), o['confidence'])
+    Kinv64 = np.linalg.inv(sc.K)
+    bgr = sc.images[ref]['image']
+    pts, col = engine.mask_backproject(r['depth'], r['confidence'], d(bgr, torch.uint8), Kinv64, sc.poses[ref][0],
+                                       sc.poses[ref][1], 2.0, 0)
+    epts, ecol = orc.mask_backproject(o['depth'], o['confidence'], bgr, Kinv64, sc.poses[ref][0], sc.poses[ref][1], 2.0, 0)
+    assert pts.shape[0] == epts.shape[0] and np.array_equal(col.cpu().numpy(), ecol)
+    np.testing.assert_allclose(pts.cpu().numpy(), epts, rtol=0, atol=1e-9)
