@@ -248,11 +248,14 @@ __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_
         for (int p = 0; p < PX; ++p) total[q][p] = 0.0f;
 
     const int lane = tid & 31;
+    const bool warp_live = y0 + (tid / 32) * (32 / NTX) * QY < H;
     if (MODE != N_STATS) mbar_wait(&bar[2], 0);
     for (int s = 0; s < S; ++s) {
         const int st = s & 1;
         mbar_wait(&bar[st], (s >> 1) & 1);
-        box_sums<K>(s_r + (1 + st) * BUF, (MODE == N_STATS) ? s_r + BUF : s_r, tx, ty, as, ass, ars);
+        // a warp owns QY*2 consecutive tile rows; in the bottom row of tiles some warps lie wholly below the image:
+        // they keep taking part in the stage hand-over but have nothing to sum or to select
+        if (warp_live) box_sums<K>(s_r + (1 + st) * BUF, (MODE == N_STATS) ? s_r + BUF : s_r, tx, ty, as, ass, ars);
         if (MODE == N_STATS) break;
         if (s + 2 < S) {
             // release the stage: one arrival per warp; the producer thread refills it once all 8 arrived
@@ -264,6 +267,7 @@ __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_
                 tma_load_2d(s_r + (1 + st) * BUF, &a.tm_s[s + 2], &bar[st], cx, cy);
             }
         }
+        if (warp_live)
 #pragma unroll
         for (int q = 0; q < QY; ++q)
 #pragma unroll
