@@ -181,7 +181,7 @@ __device__ __forceinline__ void box_sums(const float *__restrict__ s_s, const fl
         for (int p = 0; p < PX; ++p) as[q][p] = ass[q][p] = ars[q][p] = 0.0f;
     const int base = (ty * QY) * RWP + tx * PX;
     box_row<K, true, false>(s_s + base, s_r + base, as, ass, ars);
-#pragma unroll 1
+#pragma unroll 2
     for (int r = 1; r < K; ++r) box_row<K, true, true>(s_s + base + r * RWP, s_r + base + r * RWP, as, ass, ars);
     box_row<K, false, true>(s_s + base + K * RWP, s_r + base + K * RWP, as, ass, ars);
 }
