@@ -88,9 +88,9 @@ __global__ void __launch_bounds__(SBX *SBY) sample_kernel(const __grid_constant_
     float *out = a.smap + (size_t)y * a.Wp + x + a.pad;
     auto one_source = [&](int s) {
         float u, v, z, smp;
-        if (!project_sample_fast(a.cams, s, pw, a.src[s], W, wm1, hm1, rw, rh, u, v, z, smp)) {
+        if (!project_sample_fast(a.cams, s, pw, a.src[s], W, H, wm1, hm1, rw, rh, u, v, z, smp)) {
             float uv[2];
-            smp = project_sample_exact(a.cams, s, pw, a.src[s], W, wm1, hm1, uv);
+            smp = project_sample_exact(a.cams, s, pw, a.src[s], W, H, wm1, hm1, uv);
             u = uv[0];
             v = uv[1];
         }
