@@ -311,7 +311,8 @@ def main():
     ach = alg_bytes / (dom_ms * 1e-3) / 1e9
     evals = H * W * a.src                                     # (pixel, source) evaluations per launch
     fma_peak_nominal = 148 * 128 * peaks.get('sm_max_mhz', 1965.0) * 1e6 / 1e12
-    FMA_PEAK_MEASURED = 36.3                                  # T lane-FMA/s, profiles/microbench/ffma2.cu on B200
+    FMA_PEAK_MEASURED = 37.1                                  # T lane-FMA/s: best measured FFMA2 rate on this pool
+                                                              # (profiles/microbench/ffma2_issue.cu: 37.08; ffma2.cu: 36.3)
     pair_s = (dom_ms + smp_ms) * 1e-3
     fp32 = {
         'note': 'the evaluation is FP32-pipe bound, not HBM bound (SURVEY 8d); lane-ops count an FMA as one; '
@@ -329,7 +330,7 @@ def main():
     # Headline roofline of the dominant kernel against the resource that binds it: the FP32 FMA pipe.
     # Algorithmic flops of ncc_kernel per (pixel, source): three k x k window sums as FMAs (2 flops each), the two
     # products s*s and r*s, ~20 for variance / covariance / NCC / aggregation.  Peak = measured FFMA/FFMA2 rate
-    # (profiles/microbench/ffma2.cu: 36.3 T lane-FMA/s = 72.6 TFLOP/s at 1965 MHz; nominal 148*128*2*1.965 = 74.5).
+    # (profiles/microbench/ffma2_issue.cu: 37.1 T lane-FMA/s = 74.2 TFLOP/s at 1965 MHz; nominal 148*128*2*1.965 = 74.5).
     ncc_flops = evals * (6 * a.patch * a.patch + 22)
     ach_tf = ncc_flops / (dom_ms * 1e-3) / 1e12
     roofline = {'bound': 'fp32', 'achieved': ach_tf, 'peak': 2 * FMA_PEAK_MEASURED, 'unit': 'TFLOP/s',
@@ -340,7 +341,7 @@ def main():
                 'launches_timed': kernels['ncc_kernel<REFINE>']['launches_per_step'],
                 'kernel_share_of_step': kernels['ncc_kernel<REFINE>']['share_of_step'],
                 'algorithmic_flops_per_launch': ncc_flops,
-                'peak_source': 'measured FFMA rate on this pool (profiles/microbench/ffma2.cu), of measured',
+                'peak_source': 'measured FFMA2 rate on this pool (profiles/microbench/ffma2_issue.cu), of measured',
                 'how': 'CUDA events on the launching stream around every launch, one serialised step right after the '
                        'timed region',
                 'note': 'contract lists hbm|tensor; this path is neither: no dense contraction (no tensor cores) and '
@@ -412,8 +413,8 @@ def main():
                            f'parity arithmetic (BASELINE configs[2] shape)',
                  'ms_per_view': float(tms.item()) / len(refs_s),
                  'evals_per_s': gpp * 1e9 * N,
-                 'fp32_frac_parity_model': gpp * 1e9 * N * (40 + 3 * k * k) / world / 36.3e12,
-                 'fp32_frac_fast_model': gpp * 1e9 * N * (40 + 6 * (k - 1)) / world / 36.3e12}
+                 'fp32_frac_parity_model': gpp * 1e9 * N * (40 + 3 * k * k) / world / (FMA_PEAK_MEASURED * 1e12),
+                 'fp32_frac_fast_model': gpp * 1e9 * N * (40 + 6 * (k - 1)) / world / (FMA_PEAK_MEASURED * 1e12)}
 
     # ---- CPU baseline on the box's host cores (rank 0, N=1 only): the oracle on a bounded sample
     cpu = None
