@@ -10,6 +10,7 @@ import os
 
 MAX_SRC = 8
 PARITY, FAST = 0, 1
+SCHEDULE_REFERENCE, SCHEDULE_REDBLACK = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # B200DENSE_LIB selects another build of the same ABI (tuning experiments under profiles/microbench)
@@ -28,7 +29,7 @@ class Rng(C.Structure):
 
 class PmParams(C.Structure):
     _fields_ = [('patch', C.c_int32), ('iters', C.c_int32), ('samples', C.c_int32), ('arith', C.c_int32),
-                ('depth_min', C.c_double), ('depth_max', C.c_double)]
+                ('depth_min', C.c_double), ('depth_max', C.c_double), ('schedule', C.c_int32), ('reserved', C.c_int32)]
 
 
 class B200DenseError(RuntimeError):
@@ -76,8 +77,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError here = ABI mismatch; let it surface
         fn.restype = res
         fn.argtypes = args
-    if lib.b200d_abi_version() != 1:
-        raise B200DenseError(f"ABI version mismatch: library reports {lib.b200d_abi_version()}, binding expects 1")
+    if lib.b200d_abi_version() != 2:
+        raise B200DenseError(f"ABI version mismatch: library reports {lib.b200d_abi_version()}, binding expects 2")
     _lib = lib
     return lib
 

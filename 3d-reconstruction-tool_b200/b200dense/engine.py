@@ -197,12 +197,14 @@ class DenseEngine:
                 init_depth: Optional[torch.Tensor] = None, init_normal: Optional[torch.Tensor] = None,
                 rand_u: Optional[torch.Tensor] = None, rand_n: Optional[torch.Tensor] = None,
                 arith: int = _cabi.PARITY, dump_costs: bool = False, want_best: bool = False, out=None,
-                slot: int = 0):
+                slot: int = 0, schedule: int = _cabi.SCHEDULE_REFERENCE):
         """Full PatchMatch of one reference view (mvs_patchmatch.py:225-321); returns device tensors
-        dict(depth, normal, confidence[, best_cost, costs])."""
+        dict(depth, normal, confidence[, best_cost, costs]).  `schedule`: SCHEDULE_REFERENCE (the reference's two
+        shifted evaluations per iteration, bit-exact) or SCHEDULE_REDBLACK (extension: 8 checkerboard evaluations)."""
         H, W = ref.shape
         prm = PmParams(patch=patch, iters=iters, samples=samples, arith=arith,
-                       depth_min=float(depth_min), depth_max=float(depth_max))
+                       depth_min=float(depth_min), depth_max=float(depth_max), schedule=int(schedule), reserved=0)
+        per_it = (8 if schedule == _cabi.SCHEDULE_REDBLACK else 2) + samples
         rng = Rng(seed=seed, view_id=view_id, d_init_depth=_ptr(init_depth), d_init_normal=_ptr(init_normal),
                   d_rand_u=_ptr(rand_u), d_rand_n=_ptr(rand_n))
         if out is None:
@@ -210,12 +212,12 @@ class DenseEngine:
                        normal=torch.empty((H, W, 3), dtype=torch.float32, device=self.device),
                        confidence=torch.empty((H, W), dtype=torch.float32, device=self.device))
         best = torch.empty((H, W), dtype=torch.float32, device=self.device) if want_best else None
-        costs = (torch.empty((iters * (2 + samples), H, W), dtype=torch.float32, device=self.device)
+        costs = (torch.empty((iters * per_it, H, W), dtype=torch.float32, device=self.device)
                  if dump_costs else None)
         _cabi.check(self.lib.b200d_pm_view(_ptr(ref), _ptr_array(srcs), C.byref(cams), H, W, C.byref(prm), C.byref(rng),
                                            _ptr(self.scratch('view', H, W, slot)), _ptr(out['depth']), _ptr(out['normal']),
                                            _ptr(out['confidence']), _ptr(best), _ptr(costs), self._stream()))
-        self.launches += 2 + 2 * (iters * (2 + samples) + 1)    # stats, init, (sample + ncc) per evaluation
+        self.launches += 2 + 2 * (iters * per_it + 1)           # stats, init, (sample + ncc) per evaluation
         if want_best:
             out['best_cost'] = best
         if dump_costs:

@@ -366,6 +366,8 @@ int b200d_pm_view(const float *d_ref, const float *const *d_src, const b200d_cam
     if (!d_ref || !d_src || !rng || !d_scratch || !d_depth || !d_normal || !d_conf) return fail(B200D_ERR_ARG, "null pointer");
     if (prm->iters < 0 || prm->samples < 0) return fail(B200D_ERR_ARG, "negative iteration count");
     if (prm->arith != B200D_PARITY) return fail(B200D_ERR_UNSUPPORTED, "fast arithmetic not built yet");
+    if (prm->schedule != B200D_SCHEDULE_REFERENCE && prm->schedule != B200D_SCHEDULE_REDBLACK)
+        return fail(B200D_ERR_ARG, "unknown propagation schedule");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)H * W;
     const int patch = prm->patch;
@@ -405,18 +407,31 @@ int b200d_pm_view(const float *d_ref, const float *const *d_src, const b200d_cam
     a.view_id = rng->view_id;
 
     int cn = 0, e = 0;
+    a.color = -1;
+    // one shifted-neighbour evaluation: candidate = hypothesis of the pixel at (+dy,+dx); `color` restricts who may adopt it
+    auto shift_eval = [&](int dy, int dx, int color) -> int {
+        s.dy = a.dy = dy;
+        s.dx = a.dx = dx;
+        a.color = color;
+        s.eval_id = a.eval_id = (uint32_t)e;
+        TRY((launch_sample<C_SHIFT, B_PATCH>(s, st)));
+        a.normal_in = normal[cn]; a.normal_out = normal[cn ^ 1];
+        a.out = d_costs ? d_costs + (size_t)e * n : nullptr;
+        TRY(launch_ncc_k<N_SHIFT>(patch, a, st));
+        cn ^= 1; ++e;
+        return B200D_OK;
+    };
     for (int it = 0; it < prm->iters; ++it) {
-        const int sgn = (it % 2 == 0) ? 1 : -1;       // slicing semantics of :429-442
-        for (int o = 0; o < 2; ++o) {
-            s.dy = a.dy = (o == 0) ? sgn : 0;
-            s.dx = a.dx = (o == 0) ? 0 : sgn;
-            s.eval_id = a.eval_id = (uint32_t)e;
-            TRY((launch_sample<C_SHIFT, B_PATCH>(s, st)));
-            a.normal_in = normal[cn]; a.normal_out = normal[cn ^ 1];
-            a.out = d_costs ? d_costs + (size_t)e * n : nullptr;
-            TRY(launch_ncc_k<N_SHIFT>(patch, a, st));
-            cn ^= 1; ++e;
+        if (prm->schedule == B200D_SCHEDULE_REDBLACK) {
+            static const int dirs[4][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}};
+            for (int color = 0; color < 2; ++color)
+                for (int d = 0; d < 4; ++d) TRY(shift_eval(dirs[d][0], dirs[d][1], color));
+        } else {
+            const int sgn = (it % 2 == 0) ? 1 : -1;       // slicing semantics of :429-442
+            TRY(shift_eval(sgn, 0, -1));
+            TRY(shift_eval(0, sgn, -1));
         }
+        a.color = -1;
         s.dr = (float)((prm->depth_max - prm->depth_min) * pow(0.5, it));      // :466
         a.nr = (float)(0.5 * pow(0.5, it));                                    // :467
         for (int sm = 0; sm < prm->samples; ++sm) {

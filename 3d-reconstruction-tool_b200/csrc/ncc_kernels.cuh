@@ -47,6 +47,8 @@ struct NccArgs {
     float *depth_out, *normal_out, *best_out;
     float *out, *out2;                       // cost / confidence / mean1 ; var1
     int dy, dx;                              // N_SHIFT neighbour offset (candidate normal)
+    int color;                               // N_SHIFT: -1 = every pixel may adopt the candidate (reference schedule);
+                                             // 0 / 1 = only pixels with (x + y) & 1 == color (red-black extension)
     float nr;                                // N_REFINE normal range
     const float *rand_n;                     // injected N(0,1) (H,W,3) of this evaluation or NULL
     uint64_t seed;
@@ -347,7 +349,8 @@ __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_
             if (a.out) a.out[g] = cost;
             if (MODE == N_COST) continue;
             const float best = a.best_in[g];
-            const bool better = cost < best;                                                  // strict; NaN never wins
+            bool better = cost < best;                                                        // strict; NaN never wins
+            if (MODE == N_SHIFT && a.color >= 0) better = better && ((gx + gy) & 1) == a.color;
             if (better) a.depth_out[g] = __ldg(a.cand + g);
             else if (a.depth_out != a.depth_in) a.depth_out[g] = a.depth_in[g];
             if (better || a.best_out != a.best_in) a.best_out[g] = better ? cost : best;

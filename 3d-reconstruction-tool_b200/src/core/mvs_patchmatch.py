@@ -13,7 +13,8 @@ What differs, by design:
   * extra keyword-only constructor arguments: `num_src_views` (the reference hard-codes k=4 at
     :108), `rng` ('philox' = counter-based in-kernel generator; 'torch' = draw on the host with
     torch.rand/randn in the reference's call order, which makes results bit-identical to the
-    reference's CPU run under the same torch.manual_seed), `seed`, `device`.
+    reference's CPU run under the same torch.manual_seed), `seed`, `device`, and two opt-in extensions the
+    reference has no counterpart for: `consistency='geometric'` and `schedule='redblack'` (checkerboard propagation).
 """
 from __future__ import annotations
 
@@ -41,7 +42,7 @@ class PatchMatchMVS:
                  num_samples: int = 8, min_views: int = 3, depth_min: float = 0.1, depth_max: float = 100.0,
                  *, num_src_views: int = 4, rng: str = 'philox', seed: int = 0, device=None,
                  consistency: str = 'photometric', geo_min_views: int = 2, geo_px_thresh: float = 1.0,
-                 geo_rel_thresh: float = 0.01):
+                 geo_rel_thresh: float = 0.01, schedule: str = 'reference'):
         self.camera = camera
         self.scale = scale
         self.patch_size = patch_size
@@ -58,6 +59,9 @@ class PatchMatchMVS:
         if consistency not in ('photometric', 'geometric'):
             raise ValueError("consistency must be 'photometric' (the reference's check) or 'geometric' (extension)")
         self.consistency = consistency
+        if schedule not in ('reference', 'redblack'):
+            raise ValueError("schedule must be 'reference' (the reference's Jacobi shifts) or 'redblack' (extension)")
+        self.schedule = schedule
         self.geo_min_views, self.geo_px_thresh, self.geo_rel_thresh = geo_min_views, geo_px_thresh, geo_rel_thresh
         self.device = torch.device(device) if device is not None else torch.device('cuda')
         self.cache_images = True            # keep uploaded grays on the device between views
@@ -297,7 +301,8 @@ class PatchMatchMVS:
             kw = {k: v.to(eng.device, non_blocking=True).contiguous() for k, v in self._host_rng(H, W).items()}
         return eng.pm_view(ref, srcs, self._camera_block(ref_idx, src_indices, poses), self.patch_size,
                            self.num_iterations, self.num_samples, self.depth_min, self.depth_max,
-                           seed=self.seed, view_id=int(ref_idx), slot=slot, **kw)
+                           seed=self.seed, view_id=int(ref_idx), slot=slot,
+                           schedule=1 if self.schedule == 'redblack' else 0, **kw)
 
     def compute_depth_maps(self, images: Dict, poses: Dict[int, CameraPose], ref_indices: List[int] = None,
                            sources: Dict[int, List[int]] = None) -> Dict[int, DepthNormalMap]:

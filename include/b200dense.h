@@ -42,7 +42,7 @@ extern "C" {
 #endif
 
 #define B200D_MAX_SRC 8          /* source / neighbour views per reference view */
-#define B200D_ABI_VERSION 1
+#define B200D_ABI_VERSION 2
 
 typedef enum {
     B200D_OK = 0,
@@ -88,7 +88,16 @@ typedef struct {
      * are evaluated in double and then cast to fp32 (mvs_patchmatch.py:466-467); clamp and border
      * fill use the fp32 casts. */
     double depth_min, depth_max;
+    /* Propagation schedule.  B200D_SCHEDULE_REFERENCE: the reference's two whole-image shifted-neighbour evaluations
+     * per iteration (mvs_patchmatch.py:415-457) -- the graded, bit-exact mode.  B200D_SCHEDULE_REDBLACK: EXTENSION with
+     * no counterpart in the reference: per iteration, for each checkerboard colour in turn, the hypotheses of
+     * the four axis neighbours are evaluated and only pixels of that colour may adopt them (8 evaluations), so the
+     * second colour already sees the first colour's updates; refinement is unchanged. */
+    int32_t schedule;
+    int32_t reserved;
 } b200d_pm_params;
+
+typedef enum { B200D_SCHEDULE_REFERENCE = 0, B200D_SCHEDULE_REDBLACK = 1 } b200d_schedule;
 
 /* Device scratch of one view in flight, shared by all compute entry points below:
  * reference window statistics, candidate depth, validity bits, a pitch-padded copy of the reference
@@ -117,8 +126,8 @@ B200D_API int b200d_pm_cost(const float *d_ref, const float *const *d_src, const
 /* Replaces PatchMatchMVS._patchmatch_cuda (mvs_patchmatch.py:225-321) from initialisation to the
  * confidence map: init -> iters x (2 shifted-neighbour evaluations + `samples` random
  * refinements, strict `<` selection) -> confidence.  Results: d_depth (H,W), d_normal (H,W,3),
- * d_conf (H,W), optional d_best (H,W); d_scratch: b200d_scratch_bytes(H,W) bytes.  d_costs (iters*(2+samples),H,W) optional dump of every
- * evaluated cost map (tests). */
+ * d_conf (H,W), optional d_best (H,W); d_scratch: b200d_scratch_bytes(H,W) bytes.  d_costs (iters*(P+samples),H,W) optional dump of every
+ * evaluated cost map (tests), P = 2 propagation evaluations per iteration in the reference schedule, 8 in red-black. */
 B200D_API int b200d_pm_view(const float *d_ref, const float *const *d_src, const b200d_cams *cams,
                   int H, int W, const b200d_pm_params *prm, const b200d_rng *rng,
                   void *d_scratch, float *d_depth, float *d_normal, float *d_conf, float *d_best,
