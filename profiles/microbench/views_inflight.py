@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Throughput of N PatchMatch views in flight (the bench's timed step without fusion to points), for tuning runs:
-    B200D_NCC_CTAS=2 B200D_FUSE=0 python profiles/microbench/views_inflight.py [streams] [views]
-Prints views/s and, from one serialised pass, the per-tag kernel durations."""
+    B200DENSE_LIB=<variant.so> python profiles/microbench/views_inflight.py [streams] [views]
+Prints views/s and, from one serialised pass, the per-tag kernel durations.  (The B200D_NCC_CTAS / B200D_FUSE
+environment switches it echoes belonged to the rejected persistent / fused variants of
+profiles/experiments/r01_fused_persistent_mix.patch.txt; the shipped library ignores them.)"""
 import os
 import sys
 
