@@ -486,7 +486,8 @@ int b200d_plane_sweep(const float *d_ref, const float *const *d_nbr, const b200d
         s.plane_depth = depths_host[d];
         a.plane = d;
         TRY((launch_sample<C_PLANE, B_DEPTH>(s, st)));
-        TRY(launch_ncc_k<N_SWEEP>(patch, a, st));
+        if (d_ncc) TRY(launch_ncc_k<N_SWEEP_DUMP>(patch, a, st));
+        else TRY(launch_ncc_k<N_SWEEP>(patch, a, st));
     }
     return B200D_OK;
 }

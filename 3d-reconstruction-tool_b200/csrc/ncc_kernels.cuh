@@ -34,7 +34,8 @@ constexpr int TW = B200D_TW, TH = B200D_TH;                    // output tile pe
 constexpr int PX = 4, QY = 2;                                  // outputs per thread
 constexpr int NTX = TW / PX, NTY = TH / QY, NT = NTX * NTY;    // 16 x 16 threads
 
-enum NccMode { N_STATS = 0, N_COST = 1, N_CONF = 2, N_SHIFT = 3, N_REFINE = 4, N_SWEEP = 5 };
+enum NccMode { N_STATS = 0, N_COST = 1, N_CONF = 2, N_SHIFT = 3, N_REFINE = 4, N_SWEEP = 5,
+               N_SWEEP_DUMP = 6 };          // the sweep that also writes the (D,N,H,W) NCC volume (tests only)
 
 struct NccArgs {
     CUtensorMap tm_r;                        // reference gray, dims (W+PAD,H), pixel x at column x+PAD
@@ -279,26 +280,26 @@ __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_
                 const float v2 = sub(ass[q][p], mul(m2, m2));
                 const float cov = sub(ars[q][p], mul(m1v, m2));
                 const bool valid = (vb[q] >> (8 * p + s)) & 1u;
-                if (MODE == N_SWEEP) {
+                if (MODE == N_SWEEP || MODE == N_SWEEP_DUMP) {
                     // ncc = cov / sqrt(var1*var2 + 1e-8) (dense_stereo.py:344-345) is only ever compared with the
                     // threshold (:303).  The comparison is decided without the square root and the division whenever
                     // cov^2 is clearly off thresh^2 * x (0.1 % margins, four orders above the rounding errors involved);
                     // only the sliver around the threshold (and zero / negative / non-finite x) takes the exact path.
                     const float x = add(mul(v1v, v2), 1e-8f);
                     bool over;
-                    if (a.ncc) {
+                    if (MODE == N_SWEEP_DUMP) {
                         const float ncc = div_(cov, __fsqrt_rn(x));
                         const int gx = x0 + tx * PX + p, gy = y0 + ty * QY + q;
                         if (gx < W && gy < H) a.ncc[(((size_t)a.plane * S + s) * H + gy) * W + gx] = ncc;
                         over = ncc > a.thresh;
-                    } else if (!(cov > 0.0f) && a.t_lo > 0.0f) {
-                        over = false;                       // ncc <= 0, -inf or NaN; the threshold is positive
                     } else {
+                        // branch-free decision; only the undecided sliver (or a disabled quick test) takes the exact path
                         const float c2 = mul(cov, cov);
-                        const bool pos = (x > 0.0f) & (a.t_lo > 0.0f);
-                        if (pos && c2 < mul(x, a.t_lo)) over = false;
-                        else if (pos && c2 > mul(x, a.t_hi)) over = true;
-                        else over = div_(cov, __fsqrt_rn(x)) > a.thresh;
+                        const bool cpos = cov > 0.0f, xpos = x > 0.0f;                      // both false for NaN
+                        const bool sure_f = !cpos | (xpos & (c2 < mul(x, a.t_lo)));          // ncc <= 0, -inf, NaN, or clearly below
+                        const bool sure_t = cpos & xpos & (c2 > mul(x, a.t_hi));              // clearly above
+                        over = sure_t;
+                        if (!(sure_f | sure_t) | !(a.t_lo > 0.0f)) over = div_(cov, __fsqrt_rn(x)) > a.thresh;
                     }
                     if (over && valid) total[q][p] = add(total[q][p], 1.0f);                  // :303-304
                 } else {
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_
                 a.out[g] = total[q][p];
                 continue;
             }
-            if (MODE == N_SWEEP) {
+            if (MODE == N_SWEEP || MODE == N_SWEEP_DUMP) {
                 // running first-max over planes (torch.max(dim=0), dense_stereo.py:307)
                 const float prev = (a.plane == 0) ? -1.0f : a.conf[g];
                 int bi = (a.plane == 0) ? 0 : a.idx[g];

@@ -186,7 +186,7 @@ B200D_API int b200d_geo_consistency(const float *d_depth_ref, const float *const
  * this library is bracketed by CUDA events on its own stream (library-owned events, at most
  * max_records launches).  _end waits for the recorded launches, writes their durations (ms) and tags
  * (NCC kernels: mode*100 + patch with mode 0 stats, 1 cost, 2 confidence, 3 shift, 4 refine, 5 plane
- * sweep; sampling kernels: 2000 + 10*candidate + bounds; init 3000; fusion 4000) and releases the events.  Not meant to be left on in production. */
+ * sweep, 6 plane sweep with the NCC dump; sampling kernels: 2000 + 10*candidate + bounds; init 3000; fusion 4000) and releases the events.  Not meant to be left on in production. */
 B200D_API int b200d_profile_begin(int max_records);
 B200D_API int b200d_profile_end(float *ms_out, int32_t *tag_out, int cap, int *n_out);
 
