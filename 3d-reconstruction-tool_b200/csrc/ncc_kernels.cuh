@@ -270,6 +270,36 @@ __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_
                 tma_load_2d(s_r + (1 + st) * BUF, &a.tm_s[s + 2], &bar[st], cx, cy);
             }
         }
+        // PatchMatch modes: ncc = cov / (sqrt(var1*var2) + 1e-8) (mvs_patchmatch.py:410) for the eight outputs, first
+        // all of them through the branch-free fast paths (eight independent MUFU + FMA chains the compiler interleaves),
+        // then the rare untrusted ones (negative / non-finite / near-denormal operands) again with the IEEE intrinsics
+        float nccv[QY][PX];
+        if (warp_live && MODE != N_STATS && MODE != N_SWEEP && MODE != N_SWEEP_DUMP) {
+            unsigned bad = 0;
+#pragma unroll
+            for (int q = 0; q < QY; ++q)
+#pragma unroll
+                for (int p = 0; p < PX; ++p) {
+                    const float m2 = as[q][p];
+                    const float pv = mul(v1[q][p], sub(ass[q][p], mul(m2, m2)));
+                    const float cov = sub(ars[q][p], mul(m1[q][p], m2));
+                    bool t_s, t_d;
+                    const float den = add(sqrt_fast(pv, t_s), 1e-8f);                   // in [1e-8, ~1] whenever t_s holds
+                    nccv[q][p] = div_fast(cov, den, t_d);
+                    bad |= (t_s & t_d) ? 0u : 1u << (q * PX + p);
+                }
+            if (bad) {
+#pragma unroll
+                for (int q = 0; q < QY; ++q)
+#pragma unroll
+                    for (int p = 0; p < PX; ++p)
+                        if ((bad >> (q * PX + p)) & 1u) {
+                            const float m2 = as[q][p];
+                            const float pv = mul(v1[q][p], sub(ass[q][p], mul(m2, m2)));
+                            nccv[q][p] = div_(sub(ars[q][p], mul(m1[q][p], m2)), add(__fsqrt_rn(pv), 1e-8f));
+                        }
+            }
+        }
         if (warp_live)
 #pragma unroll
         for (int q = 0; q < QY; ++q)
@@ -303,8 +333,7 @@ __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_
                     }
                     if (over && valid) total[q][p] = add(total[q][p], 1.0f);                  // :303-304
                 } else {
-                    const float ncc = div_(cov, add(__fsqrt_rn(mul(v1v, v2)), 1e-8f));   // mvs_patchmatch.py:410
-                    const float cost = sub(1.0f, ncc);
+                    const float cost = sub(1.0f, nccv[q][p]);
                     if (MODE == N_CONF) {
                         const float ncc2 = sub(1.0f, cost);                                   // :530
                         if (valid && (ncc2 > 0.6f)) total[q][p] = add(total[q][p], 1.0f);
