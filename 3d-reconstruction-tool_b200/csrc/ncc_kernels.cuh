@@ -346,6 +346,29 @@ __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_
     }
 
     // ---- epilogue
+    // avg = total / (count + 1e-8) (:387) for the eight outputs, batched through the branch-free division like the NCC
+    // above (the divisor is 1e-8, 1, 2, ..., S: always a trusted one)
+    float avgv[QY][PX];
+    if (MODE == N_COST || MODE == N_SHIFT || MODE == N_REFINE) {
+        unsigned bad = 0;
+#pragma unroll
+        for (int q = 0; q < QY; ++q)
+#pragma unroll
+            for (int p = 0; p < PX; ++p) {
+                const float cntf = (float)((cnt >> (4 * (q * PX + p))) & 15u);
+                bool t;
+                avgv[q][p] = div_fast(total[q][p], add(cntf, 1e-8f), t);
+                bad |= t ? 0u : 1u << (q * PX + p);
+            }
+        if (bad) {
+#pragma unroll
+            for (int q = 0; q < QY; ++q)
+#pragma unroll
+                for (int p = 0; p < PX; ++p)
+                    if ((bad >> (q * PX + p)) & 1u)
+                        avgv[q][p] = div_(total[q][p], add((float)((cnt >> (4 * (q * PX + p))) & 15u), 1e-8f));
+        }
+    }
     unsigned wins = 0;                                     // N_REFINE: bit q*PX+p = output (q,p) of this thread won
 #pragma unroll
     for (int q = 0; q < QY; ++q)
@@ -374,7 +397,7 @@ __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_
                 continue;
             }
             const float cntf = (float)((cnt >> (4 * (q * PX + p))) & 15u);
-            const float avg = div_(total[q][p], add(cntf, 1e-8f));                            // :387
+            const float avg = avgv[q][p];                                                     // :387
             const float cost = (cntf >= 2.0f) ? avg : __int_as_float(0x7f800000);            // :388
             if (a.out) a.out[g] = cost;
             if (MODE == N_COST) continue;
