@@ -46,7 +46,7 @@ constexpr int SBX = 32, SBY = 8;         // thread block: 32 x 8 pixels
 // constant-bank operand of the arithmetic instruction that uses it (no uniform loads, no index arithmetic);
 // NS == 0: run-time count.
 template <int CAND, int BOUNDS, int NS>
-__global__ void __launch_bounds__(SBX *SBY) sample_kernel(const __grid_constant__ SampleArgs a) {
+__global__ void __launch_bounds__(SBX *SBY, 6) sample_kernel(const __grid_constant__ SampleArgs a) {
     const int x = blockIdx.x * SBX + threadIdx.x, y = blockIdx.y * SBY + threadIdx.y;
     if (x >= a.W || y >= a.H) return;
     const int W = a.W, H = a.H;
