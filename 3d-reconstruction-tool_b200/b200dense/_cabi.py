@@ -52,6 +52,7 @@ PROTOTYPES = {
     'b200d_plane_sweep': (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(Cams), C.POINTER(C.c_float), _i, _i, _i, _i, _f, _i,
                                     _vp, _vp, _vp, _vp, _vp, _vp]),
     'b200d_knn_mean_dist': (C.c_int, [_vp, C.c_int64, _i, _vp, _vp]),
+    'b200d_selftest_fast_math': (C.c_int, [C.c_uint64, C.POINTER(C.c_uint64), _vp]),
     'b200d_prepare_image': (C.c_int, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'b200d_write_ply_ascii': (C.c_int, [C.c_char_p, _dp, C.POINTER(C.c_uint8), C.c_int64]),
     'b200d_geo_consistency': (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(Cams), _i, _i, _f, _f, _vp, _vp]),

@@ -522,6 +522,58 @@ int b200d_knn_mean_dist(const double *d_points, int64_t n, int k, double *d_mean
     return cuda_check(cudaGetLastError(), "knn_mean_dist_kernel launch");
 }
 
+// ---- self-test of the branch-free IEEE helpers (device_math.cuh): every trusted result must equal the intrinsic's
+namespace {
+__global__ void selftest_sqrt_kernel(unsigned long long *bad, unsigned long long *trusted_n) {
+    unsigned long long nb = 0, nt = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 32);
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((unsigned)i);
+        bool t;
+        const float f = sqrt_fast(x, t);
+        if (t) {
+            ++nt;
+            if (__float_as_uint(f) != __float_as_uint(__fsqrt_rn(x))) ++nb;
+        }
+    }
+    if (nb) atomicAdd(bad, nb);
+    atomicAdd(trusted_n, nt);
+}
+__global__ void selftest_div_kernel(unsigned long long *bad, unsigned long long *trusted_n, unsigned long long n) {
+    unsigned long long nb = 0, nt = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 7u, 9u), make_uint2(1u, 2u));
+        const float a = __uint_as_float(r.x);                                   // any bit pattern
+        // divisors of the two call sites: sqrt(..) + 1e-8 in [1e-8, 4) and count + 1e-8 in {1e-8, 1, ..., 8}
+        const float b = (r.w & 1u) ? 1e-8f + u01(r.y) * ((r.w & 2u) ? 4.0f : 1e-4f) : (float)(r.z % 9u) + 1e-8f;
+        bool t;
+        const float f = div_fast(a, b, t);
+        if (t) {
+            ++nt;
+            if (__float_as_uint(f) != __float_as_uint(__fdiv_rn(a, b))) ++nb;
+        }
+    }
+    if (nb) atomicAdd(bad, nb);
+    atomicAdd(trusted_n, nt);
+}
+}  // namespace
+
+int b200d_selftest_fast_math(uint64_t n_div, uint64_t *out4, void *stream) {
+    if (!out4) return fail(B200D_ERR_ARG, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 4 * sizeof(unsigned long long)));
+    cudaMemsetAsync(d, 0, 4 * sizeof(unsigned long long), st);
+    selftest_sqrt_kernel<<<148 * 8, 256, 0, st>>>(d + 0, d + 1);
+    selftest_div_kernel<<<148 * 8, 256, 0, st>>>(d + 2, d + 3, (unsigned long long)n_div);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out4, d, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    return cuda_check(e, "fast-math self-test");
+}
+
 int b200d_prepare_image(const uint8_t *d_bgr, int H, int W, int nh, int nw, const int32_t *d_xi, const int16_t *d_xa,
                         const int32_t *d_yi, const int16_t *d_ya, uint8_t *d_color, float *d_gray, void *stream) {
     if (H < 1 || W < 1 || nh < 1 || nw < 1) return fail(B200D_ERR_ARG, "empty image");
