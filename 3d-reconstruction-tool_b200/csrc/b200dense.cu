@@ -557,18 +557,41 @@ __global__ void selftest_div_kernel(unsigned long long *bad, unsigned long long 
     if (nb) atomicAdd(bad, nb);
     atomicAdd(trusted_n, nt);
 }
+// the sampling kernel's shared-reciprocal divisions: operands inside the range guard -> same bits as __fdiv_rn; and the
+// relaxed case of the constant divisors W-1 / H-1: a numerator below the guard (incl. zero and denormals) may give an
+// inexact quotient, but `quotient - 1` -- all the kernel uses -- must not change
+__global__ void selftest_sample_div_kernel(unsigned long long *out, unsigned long long n) {
+    unsigned long long nb = 0, nt = 0, rb = 0, rt = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 11u, 13u), make_uint2(3u, 4u));
+        const float a = __uint_as_float(r.x), b = __uint_as_float(r.y);
+        if (in_range(a) && in_range(b)) {
+            ++nt;
+            if (__float_as_uint(div_rcp(a, b, rcp_refined(b))) != __float_as_uint(__fdiv_rn(a, b))) ++nb;
+        }
+        const float wm1 = (float)(1u + (r.z & 0xffffffu));                      // W-1 in [1, 2^24]
+        const float rw = rcp_refined(wm1);
+        if (fabsf(a) < 0x1p40f) {                                               // the relaxed guard (upper bound only)
+            ++rt;
+            if (__float_as_uint(sub(div_rcp(a, wm1, rw), 1.0f)) != __float_as_uint(sub(__fdiv_rn(a, wm1), 1.0f))) ++rb;
+        }
+    }
+    atomicAdd(out + 0, nb); atomicAdd(out + 1, nt); atomicAdd(out + 2, rb); atomicAdd(out + 3, rt);
+}
 }  // namespace
 
-int b200d_selftest_fast_math(uint64_t n_div, uint64_t *out4, void *stream) {
-    if (!out4) return fail(B200D_ERR_ARG, "null pointer");
+int b200d_selftest_fast_math(uint64_t n_div, uint64_t *out8, void *stream) {
+    if (!out8) return fail(B200D_ERR_ARG, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long *d = nullptr;
-    CUDA_TRY(cudaMalloc(&d, 4 * sizeof(unsigned long long)));
-    cudaMemsetAsync(d, 0, 4 * sizeof(unsigned long long), st);
+    CUDA_TRY(cudaMalloc(&d, 8 * sizeof(unsigned long long)));
+    cudaMemsetAsync(d, 0, 8 * sizeof(unsigned long long), st);
     selftest_sqrt_kernel<<<148 * 8, 256, 0, st>>>(d + 0, d + 1);
     selftest_div_kernel<<<148 * 8, 256, 0, st>>>(d + 2, d + 3, (unsigned long long)n_div);
+    selftest_sample_div_kernel<<<148 * 8, 256, 0, st>>>(d + 4, (unsigned long long)n_div);
     cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out4, d, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out8, d, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(d);
     return cuda_check(e, "fast-math self-test");

@@ -185,9 +185,11 @@ B200D_API int b200d_geo_consistency(const float *d_depth_ref, const float *const
 /* Diagnostic (synchronises): checks the branch-free IEEE sqrt / division helpers the NCC epilogue uses against the
  * compiler's __fsqrt_rn / __fdiv_rn -- the square root over all 2^32 bit patterns, the division over n_div
  * pseudo-random (numerator, divisor) pairs with any numerator and the divisors its two call sites produce.
- * out4 (HOST) = {sqrt mismatches among trusted results, trusted sqrt results, division mismatches, trusted divisions};
- * untrusted results are the ones the kernels redo with the intrinsics. */
-B200D_API int b200d_selftest_fast_math(uint64_t n_div, uint64_t *out4, void *stream);
+ * out8 (HOST) = {sqrt mismatches among trusted results, trusted sqrt results, division mismatches, trusted divisions,
+ * mismatches / count of the sampling kernel's shared-reciprocal division inside its range guard, mismatches / count of
+ * `a / (W-1) - 1` under the relaxed (upper-bound-only) guard}; untrusted results are the ones the kernels redo with
+ * the intrinsics. */
+B200D_API int b200d_selftest_fast_math(uint64_t n_div, uint64_t *out8, void *stream);
 
 /* Optional per-launch timing for benchmarks.  Between _begin and _end every tile kernel launched by
  * this library is bracketed by CUDA events on its own stream (library-owned events, at most
