@@ -9,8 +9,10 @@ import ctypes as C
 import os
 
 MAX_SRC = 8
-PARITY, FAST = 0, 1
+PARITY, FAST, PARITY_CHAINS = 0, 1, 2
 SCHEDULE_REFERENCE, SCHEDULE_REDBLACK = 0, 1
+STAGE_NO_INIT, STAGE_NO_CONF = 1, 2
+ABI_VERSION = 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # B200DENSE_LIB selects another build of the same ABI (tuning experiments under profiles/microbench)
@@ -29,7 +31,8 @@ class Rng(C.Structure):
 
 class PmParams(C.Structure):
     _fields_ = [('patch', C.c_int32), ('iters', C.c_int32), ('samples', C.c_int32), ('arith', C.c_int32),
-                ('depth_min', C.c_double), ('depth_max', C.c_double), ('schedule', C.c_int32), ('reserved', C.c_int32)]
+                ('depth_min', C.c_double), ('depth_max', C.c_double), ('schedule', C.c_int32), ('stage', C.c_int32),
+                ('it_begin', C.c_int32), ('it_end', C.c_int32)]
 
 
 class B200DenseError(RuntimeError):
@@ -49,15 +52,20 @@ PROTOTYPES = {
     'b200d_pm_cost': (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(Cams), _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     'b200d_pm_view': (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(Cams), _i, _i, C.POINTER(PmParams), C.POINTER(Rng),
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'b200d_pm_viewprop': (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(Cams), _i, _i, C.POINTER(PmParams), C.POINTER(_vp),
+                                    C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp]),
+    'b200d_sweep_fallbacks': (C.c_int, [C.POINTER(C.c_uint64), _i]),
     'b200d_plane_sweep': (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(Cams), C.POINTER(C.c_float), _i, _i, _i, _i, _f, _i,
                                     _vp, _vp, _vp, _vp, _vp, _vp]),
     'b200d_knn_mean_dist': (C.c_int, [_vp, C.c_int64, _i, _vp, _vp]),
     'b200d_selftest_fast_math': (C.c_int, [C.c_uint64, C.POINTER(C.c_uint64), _vp]),
+    'b200d_measure_fp32_peak': (C.c_int, [_dp, _vp]),
     'b200d_prepare_image': (C.c_int, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'b200d_write_ply_ascii': (C.c_int, [C.c_char_p, _dp, C.POINTER(C.c_uint8), C.c_int64]),
     'b200d_geo_consistency': (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(Cams), _i, _i, _f, _f, _vp, _vp]),
     'b200d_profile_begin': (C.c_int, [_i]),
     'b200d_profile_end': (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32), _i, C.POINTER(C.c_int)]),
+    'b200d_mask_count': (C.c_int, [_vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp]),
     'b200d_mask_backproject': (C.c_int, [_vp, _vp, _vp, _i, _i, _dp, _dp, _dp, _f, _i, _vp, _vp, _vp, _vp, _vp]),
 }
 
@@ -78,8 +86,9 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError here = ABI mismatch; let it surface
         fn.restype = res
         fn.argtypes = args
-    if lib.b200d_abi_version() != 2:
-        raise B200DenseError(f"ABI version mismatch: library reports {lib.b200d_abi_version()}, binding expects 2")
+    if lib.b200d_abi_version() != ABI_VERSION:
+        raise B200DenseError(f"ABI version mismatch: library reports {lib.b200d_abi_version()}, "
+                             f"binding expects {ABI_VERSION}")
     _lib = lib
     return lib
 

@@ -39,6 +39,50 @@ def owner_of(position: int, world_size: int) -> int:
     return position % world_size
 
 
+def exchange_counts(n_positions: int, local_counts: Dict[int, int], device: torch.device) -> List[int]:
+    """Point counts of all `n_positions` views on every rank (host ints).  `local_counts` maps this rank's positions
+    (indices into the sorted view list) to their counts; every position has exactly one owner, so one all-reduce of a
+    small integer vector does it."""
+    rank, ws = world()
+    host = torch.zeros(n_positions, dtype=torch.int64)
+    for pos, c in local_counts.items():
+        host[pos] = int(c)
+    if ws == 1:
+        return host.tolist()
+    counts = host.to(device)
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    return counts.cpu().tolist()
+
+
+def gather_into(counts: Sequence[int], local: Dict[int, Tuple[torch.Tensor, torch.Tensor]],
+                out_points: torch.Tensor = None, out_colors: torch.Tensor = None) -> None:
+    """Collect the per-view clouds on rank 0 without staging copies.
+
+    `counts[pos]` is the point count of the view at `pos` of the sorted view list (exchange_counts).  On rank 0
+    `out_points` (sum(counts),3) f64 / `out_colors` (sum(counts),3) u8 are the final buffers in the reference's vstack
+    order (mvs_patchmatch.py:544-570); rank 0's own views are expected to be in place already (its back-projection
+    kernels wrote into those slices).  Every other rank sends the slice of each of its non-empty views
+    (`local[pos]` = (points, colours), contiguous); rank 0 receives straight into the final slices.  One batch of
+    point-to-point operations (NCCL over NVLink on GPUs; gloo in the CPU tests)."""
+    rank, ws = world()
+    if ws == 1:
+        return
+    ops, off = [], 0
+    for pos, m in enumerate(counts):
+        m = int(m)
+        owner = owner_of(pos, ws)
+        if m and owner != 0:
+            if rank == 0:
+                ops += [dist.P2POp(dist.irecv, out_points[off:off + m], owner),
+                        dist.P2POp(dist.irecv, out_colors[off:off + m], owner)]
+            elif rank == owner:
+                ops += [dist.P2POp(dist.isend, local[pos][0], 0), dist.P2POp(dist.isend, local[pos][1], 0)]
+        off += m
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
 def gather_point_clouds(views: Sequence[int], local: Dict[int, Tuple[torch.Tensor, torch.Tensor]],
                         device: torch.device) -> Tuple[torch.Tensor, torch.Tensor]:
     """Collect per-view (points (M,3) f64, colors (M,3) u8) on rank 0, concatenated in `views` order.

@@ -48,15 +48,30 @@ class PinnedPool:
     more than the PatchMatch of the view it carries -- so buffers are pooled by (shape, dtype).  A result array
     handed to the caller owns its buffer; when the array is garbage-collected the buffer returns to the pool."""
 
-    def __init__(self):
+    def __init__(self, max_idle_bytes: int = 2 << 30):
         self._free: Dict[Tuple[Tuple[int, ...], torch.dtype], List[torch.Tensor]] = {}
+        self.max_idle_bytes = max_idle_bytes      # idle (returned) buffers kept for reuse; beyond it they are released
+        self._idle_bytes = 0
 
     def take(self, shape, dtype) -> torch.Tensor:
         lst = self._free.get((tuple(shape), dtype))
-        return lst.pop() if lst else torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
+        if lst:
+            t = lst.pop()
+            self._idle_bytes -= t.numel() * t.element_size()
+            return t
+        return torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
 
     def _give(self, t: torch.Tensor) -> None:
+        nbytes = t.numel() * t.element_size()
+        if self._idle_bytes + nbytes > self.max_idle_bytes:
+            return                                # dropped: the page-locked allocation is freed with the tensor
+        self._idle_bytes += nbytes
         self._free.setdefault((tuple(t.shape), t.dtype), []).append(t)
+
+    def trim(self) -> None:
+        """Release every idle buffer."""
+        self._free.clear()
+        self._idle_bytes = 0
 
     def as_numpy(self, t: torch.Tensor) -> np.ndarray:
         a = t.numpy()
@@ -72,6 +87,19 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
         return None
     assert t.is_cuda and t.is_contiguous(), "device tensors must be contiguous CUDA tensors"
     return t.data_ptr()
+
+
+def _tensors_of(obj):
+    """CUDA tensors inside a job result (tensor / dict / tuple / list, nested)."""
+    if isinstance(obj, torch.Tensor):
+        if obj.is_cuda:
+            yield obj
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            yield from _tensors_of(v)
+    elif isinstance(obj, (tuple, list)):
+        for v in obj:
+            yield from _tensors_of(v)
 
 
 def _ptr_array(ts: Sequence[torch.Tensor]):
@@ -147,16 +175,24 @@ class DenseEngine:
         start = torch.cuda.Event()
         start.record(main)
         results = []
-        for j, job in enumerate(jobs):
-            st = self._streams[j % n]
-            if j < n:
-                st.wait_event(start)
-            with torch.cuda.stream(st):
-                results.append(job(j % n))
-        for st in self._streams[:n]:
-            done = torch.cuda.Event()
-            done.record(st)
-            main.wait_event(done)
+        try:
+            for j, job in enumerate(jobs):
+                st = self._streams[j % n]
+                if j < n:
+                    st.wait_event(start)
+                with torch.cuda.stream(st):
+                    results.append(job(j % n))
+        finally:
+            # also when a job raised: the caller's stream must not run ahead of (or free buffers under) the
+            # kernels already enqueued on the side streams
+            for st in self._streams[:n]:
+                done = torch.cuda.Event()
+                done.record(st)
+                main.wait_event(done)
+        # results were allocated on side streams and are consumed on the caller's stream from here on
+        for r in results:
+            for t in _tensors_of(r):
+                t.record_stream(main)
         return results
 
     # ------------------------------------------------------------------ per-launch timing (benchmarks)
@@ -197,13 +233,17 @@ class DenseEngine:
                 init_depth: Optional[torch.Tensor] = None, init_normal: Optional[torch.Tensor] = None,
                 rand_u: Optional[torch.Tensor] = None, rand_n: Optional[torch.Tensor] = None,
                 arith: int = _cabi.PARITY, dump_costs: bool = False, want_best: bool = False, out=None,
-                slot: int = 0, schedule: int = _cabi.SCHEDULE_REFERENCE):
+                slot: int = 0, schedule: int = _cabi.SCHEDULE_REFERENCE, it_begin: int = 0, it_end: int = 0,
+                stage: int = 0, costs: Optional[torch.Tensor] = None):
         """Full PatchMatch of one reference view (mvs_patchmatch.py:225-321); returns device tensors
         dict(depth, normal, confidence[, best_cost, costs]).  `schedule`: SCHEDULE_REFERENCE (the reference's two
-        shifted evaluations per iteration, bit-exact) or SCHEDULE_REDBLACK (extension: 8 checkerboard evaluations)."""
+        shifted evaluations per iteration, bit-exact) or SCHEDULE_REDBLACK (extension: 8 checkerboard evaluations).
+        Staged execution (`it_begin`, `it_end`, `stage` flags STAGE_NO_INIT / STAGE_NO_CONF): run part of the view on
+        the state held in `out` (which must then carry 'best_cost'); used by the view-propagation schedule."""
         H, W = ref.shape
         prm = PmParams(patch=patch, iters=iters, samples=samples, arith=arith,
-                       depth_min=float(depth_min), depth_max=float(depth_max), schedule=int(schedule), reserved=0)
+                       depth_min=float(depth_min), depth_max=float(depth_max), schedule=int(schedule), stage=int(stage),
+                       it_begin=int(it_begin), it_end=int(it_end))
         per_it = (8 if schedule == _cabi.SCHEDULE_REDBLACK else 2) + samples
         rng = Rng(seed=seed, view_id=view_id, d_init_depth=_ptr(init_depth), d_init_normal=_ptr(init_normal),
                   d_rand_u=_ptr(rand_u), d_rand_n=_ptr(rand_n))
@@ -211,18 +251,52 @@ class DenseEngine:
             out = dict(depth=torch.empty((H, W), dtype=torch.float32, device=self.device),
                        normal=torch.empty((H, W, 3), dtype=torch.float32, device=self.device),
                        confidence=torch.empty((H, W), dtype=torch.float32, device=self.device))
-        best = torch.empty((H, W), dtype=torch.float32, device=self.device) if want_best else None
-        costs = (torch.empty((iters * per_it, H, W), dtype=torch.float32, device=self.device)
-                 if dump_costs else None)
+        best = out.get('best_cost')
+        if best is None and want_best:
+            best = torch.empty((H, W), dtype=torch.float32, device=self.device)
+        if costs is None and dump_costs:
+            costs = torch.empty((iters * per_it, H, W), dtype=torch.float32, device=self.device)
         _cabi.check(self.lib.b200d_pm_view(_ptr(ref), _ptr_array(srcs), C.byref(cams), H, W, C.byref(prm), C.byref(rng),
                                            _ptr(self.scratch('view', H, W, slot)), _ptr(out['depth']), _ptr(out['normal']),
                                            _ptr(out['confidence']), _ptr(best), _ptr(costs), self._stream()))
-        self.launches += 2 + 2 * (iters * per_it + 1)           # stats, init, (sample + ncc) per evaluation
-        if want_best:
+        n_it = (it_end if it_end > 0 else iters) - it_begin
+        # stats, [init], (sample + ncc) per evaluation, [confidence pair]
+        self.launches += 1 + (0 if stage & _cabi.STAGE_NO_INIT else 1) + 2 * n_it * per_it + \
+            (0 if stage & _cabi.STAGE_NO_CONF else 2)
+        if best is not None:
             out['best_cost'] = best
-        if dump_costs:
+        if costs is not None:
             out['costs'] = costs
         return out
+
+    def pm_viewprop(self, ref: torch.Tensor, srcs: Sequence[torch.Tensor], cams: Cams, patch: int, depth_min: float,
+                    depth_max: float, src_depth: Sequence[torch.Tensor], src_normal: Sequence[torch.Tensor], state: dict,
+                    *, arith: int = _cabi.PARITY, dump_costs: bool = False, slot: int = 0):
+        """EXTENSION: one view-propagation step (b200d_pm_viewprop) on `state` = dict(depth, normal, best_cost), in
+        place, from snapshots of the source views' depth / normal maps.  Returns the (S,H,W) cost dump if asked."""
+        H, W = ref.shape
+        prm = PmParams(patch=patch, iters=0, samples=0, arith=arith, depth_min=float(depth_min),
+                       depth_max=float(depth_max), schedule=0, stage=0, it_begin=0, it_end=0)
+        costs = torch.empty((len(srcs), H, W), dtype=torch.float32, device=self.device) if dump_costs else None
+        _cabi.check(self.lib.b200d_pm_viewprop(_ptr(ref), _ptr_array(srcs), C.byref(cams), H, W, C.byref(prm),
+                                               _ptr_array(src_depth), _ptr_array(src_normal),
+                                               _ptr(self.scratch('view', H, W, slot)), _ptr(state['depth']),
+                                               _ptr(state['normal']), _ptr(state['best_cost']), _ptr(costs),
+                                               self._stream()))
+        self.launches += 1 + 3 * len(srcs)
+        return costs
+
+    def measure_fp32_peak(self) -> float:
+        """Sustained FFMA2 rate of this GPU in T lane-FMA/s (synchronises; benchmarks' roofline denominator)."""
+        v = C.c_double(0.0)
+        _cabi.check(self.lib.b200d_measure_fp32_peak(C.byref(v), self._stream()))
+        return float(v.value)
+
+    def sweep_fallbacks(self, reset: bool = False) -> int:
+        """(warp, neighbour) evaluations of the bounded plane sweep redone with the exact chains (synchronises)."""
+        n = C.c_uint64(0)
+        _cabi.check(self.lib.b200d_sweep_fallbacks(C.byref(n), 1 if reset else 0))
+        return int(n.value)
 
     def plane_sweep(self, ref: torch.Tensor, nbrs: Sequence[torch.Tensor], cams: Cams, depths: np.ndarray,
                     patch: int, thresh: float, arith: int = _cabi.PARITY, dump_ncc: bool = False, slot: int = 0):
@@ -278,10 +352,19 @@ class DenseEngine:
         self.launches += 1
         return color, gray
 
+    def mask_count(self, depth: torch.Tensor, conf: torch.Tensor, min_conf: float, mode: int, count: torch.Tensor,
+                   slot: int = 0) -> torch.Tensor:
+        """Count-only pass of the fusion mask into `count` (1-element int64 device tensor); nothing is read back."""
+        H, W = depth.shape
+        _cabi.check(self.lib.b200d_mask_count(_ptr(depth), _ptr(conf), H, W, float(min_conf), mode, _ptr(count),
+                                              _ptr(self.scratch('fuse', H, W, slot)), self._stream()))
+        self.launches += 2
+        return count
+
     def mask_backproject(self, depth: torch.Tensor, conf: torch.Tensor, bgr: torch.Tensor, Kinv64: np.ndarray,
                          R: np.ndarray, t: np.ndarray, min_conf: float, mode: int,
                          points: Optional[torch.Tensor] = None, colors: Optional[torch.Tensor] = None,
-                         sync: bool = True, slot: int = 0):
+                         sync: bool = True, slot: int = 0, count: Optional[torch.Tensor] = None):
         """Mask + ordered compaction + back-projection (mvs_patchmatch.py:545-565 / dense_stereo.py:414-437).
         Returns (points (M,3) f64, colors (M,3) u8) device tensors; synchronises to read M.
         With sync=False nothing is read back: returns (points buffer, colors buffer, count tensor)."""
@@ -290,7 +373,8 @@ class DenseEngine:
             points = torch.empty((H * W, 3), dtype=torch.float64, device=self.device)
         if colors is None:
             colors = torch.empty((H * W, 3), dtype=torch.uint8, device=self.device)
-        count = torch.zeros(1, dtype=torch.int64, device=self.device)
+        if count is None:
+            count = torch.zeros(1, dtype=torch.int64, device=self.device)
         Ki = np.ascontiguousarray(Kinv64, dtype=np.float64)
         Rm = np.ascontiguousarray(R, dtype=np.float64)
         tv = np.ascontiguousarray(t, dtype=np.float64).ravel()

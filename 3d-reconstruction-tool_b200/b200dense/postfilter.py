@@ -4,7 +4,11 @@ The reference runs these in NumPy on one CPU core over the whole fused cloud
 (`PatchMatchMVS._filter_points`, src/core/mvs_patchmatch.py:572-588;
 `DenseStereoReconstructor._voxel_down_sample`, src/core/dense_stereo.py:475-492).  At the benchmark
 scales (tens of millions of points) they dwarf the GPU stage, so they are restated here as device-side
-tensor programs: sorts / scans from the library (torch -> CUB radix sort), everything kept in f64.
+tensor programs: sorts / scans from the library (torch -> CUB radix sort), everything kept in f64, no scalar read
+back to the host in between (the only synchronisations are the two boolean-mask compactions, whose output sizes the
+host must know).  Decision recorded in DESIGN.md 5.4: the voxel de-duplication stays on the library's radix sort --
+it is an HBM-bound LSD radix sort of (key, index) pairs that already runs at the memory roofline; a hand-written
+replacement would be the same algorithm (bench.py --config full4k reports its share of the stage).
 The semantics are reproduced exactly, including NumPy's conventions:
 
   np.median        mean of the two middle order statistics for even n
@@ -32,22 +36,21 @@ def _median_axis0(x: torch.Tensor) -> torch.Tensor:
     return (s[n // 2 - 1] + s[n // 2]) / 2.0
 
 
-def _percentile_linear(sorted_vals: torch.Tensor, q_percent: float) -> float:
-    """np.percentile(v, q) with the default 'linear' method, from the sorted values (f64)."""
+def _percentile_linear(sorted_vals: torch.Tensor, q_percent: float) -> torch.Tensor:
+    """np.percentile(v, q) with the default 'linear' method, from the sorted values (f64): a 0-dim tensor on the
+    values' device -- nothing is read back to the host (the indices and the interpolation weight depend on n only)."""
     n = int(sorted_vals.shape[0])
     q = np.true_divide(q_percent, 100)
     vi = (n - 1) * q                                            # numpy 'linear': get_virtual_index
     if vi >= n - 1:                                             # _get_indexes: above bounds -> the maximum
-        return float(sorted_vals[n - 1].item())
+        return sorted_vals[n - 1]
     lo = int(np.floor(vi))
-    gamma = np.float64(vi - lo)
-    a = np.float64(sorted_vals[lo].item())
-    b = np.float64(sorted_vals[lo + 1].item())
-    diff = b - a                                                # numpy _lerp
-    out = a + diff * gamma
+    gamma = float(np.float64(vi - lo))
+    a, b = sorted_vals[lo], sorted_vals[lo + 1]
+    diff = b - a                                                # numpy _lerp: separate multiply and add, in f64
     if gamma >= 0.5:
-        out = b - diff * (1 - gamma)
-    return float(out)
+        return b - diff * (1 - gamma)
+    return a + diff * gamma
 
 
 def _first_of_each_voxel(points: torch.Tensor, voxel_size: float, cast_int32: bool) -> torch.Tensor:

@@ -5,13 +5,19 @@
 //   sample_kernel  (sample_kernels.cuh)  candidate depth -> reproject -> bilinear sample, per pixel
 //   ncc_kernel     (ncc_kernels.cuh)     TMA-fed tiles -> K x K window sums (FFMA2) -> NCC -> select
 // The sampled images sit in an L2-sized scratch between the two.
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "b200dense.h"
+#include "diag_kernels.cuh"
+#include "fast_kernels.cuh"
 #include "fuse_kernels.cuh"
 #include "geo_kernels.cuh"
 #include "knn_kernels.cuh"
@@ -77,13 +83,13 @@ struct ProfScope {
 // ---- scratch layout shared by all entry points (one slot = one view in flight)
 struct Scratch {
     float *mean1, *var1, *cand, *best, *normal_alt, *rpad, *smap;
-    uint8_t *valid;
+    uint8_t *valid, *allow;
     int Wp;
     size_t map_stride;           // floats between consecutive sampled maps
     static int pitch(int W) { return (W + 3 + 3) / 4 * 4; }     // room for the largest column offset (PAD <= 3)
     static size_t bytes(int H, int W) {
         const size_t n = (size_t)H * W, np = (size_t)H * pitch(W);
-        return 4 * align256(n * 4) + align256(3 * n * 4) + align256(n) + align256(np * 4) +
+        return 4 * align256(n * 4) + align256(3 * n * 4) + 2 * align256(n) + align256(np * 4) +
                B200D_MAX_SRC * align256(np * 4);
     }
     Scratch(void *base, int H, int W) {
@@ -96,6 +102,7 @@ struct Scratch {
         best = (float *)take(n * 4);
         normal_alt = (float *)take(3 * n * 4);
         valid = (uint8_t *)take(n);
+        allow = (uint8_t *)take(n);
         rpad = (float *)take(np * 4);
         smap = (float *)take(np * 4);
         Wp = pitch(W);
@@ -109,13 +116,18 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int make_tensor_map(CUtensorMap *m, const float *base, int W, int H, size_t pitch_floats, int box_w, int box_h) {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
+    // resolved once per process; C++11 guarantees the initialisation of a function-local static is thread-safe
+    static const EncodeTiledFn fn = [] {
         void *p = nullptr;
         cudaDriverEntryPointQueryResult q;
-        CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
-        if (!p || q != cudaDriverEntryPointSuccess) return fail(B200D_ERR_CUDA, "cuTensorMapEncodeTiled not available");
-        fn = (EncodeTiledFn)p;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    if (!fn) {
+        cudaGetLastError();
+        return fail(B200D_ERR_CUDA, "cuTensorMapEncodeTiled not available");
     }
     const cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)H};
     const cuuint64_t strides[1] = {(cuuint64_t)pitch_floats * sizeof(float)};
@@ -162,14 +174,23 @@ int prepare_tma(int patch, const float *d_ref, int H, int W, int S, const Scratc
     return B200D_OK;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device (and per kernel): one bit per device ordinal, set once
+template <typename Kern>
+int ensure_smem(Kern kern, std::atomic<uint64_t> &configured, size_t bytes) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        configured.fetch_or(bit, std::memory_order_release);
+    }
+    return B200D_OK;
+}
+
 template <int K, int MODE>
 int launch_ncc(const NccArgs &a, cudaStream_t st) {
-    static bool configured = false;          // per instantiation; the attribute is idempotent
-    if (!configured) {
-        CUDA_TRY(cudaFuncSetAttribute(ncc_kernel<K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)Geo<K>::smem_bytes));
-        configured = true;
-    }
+    static std::atomic<uint64_t> configured{0};
+    TRY(ensure_smem(ncc_kernel<K, MODE>, configured, Geo<K>::smem_bytes));
     ProfScope prof(MODE * 100 + K, st);
     const dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, 1);
     ncc_kernel<K, MODE><<<grid, NT, Geo<K>::smem_bytes, st>>>(a);
@@ -189,6 +210,30 @@ int launch_ncc_k(int patch, const NccArgs &a, cudaStream_t st) {
     }
 }
 
+// separable-sum kernels (fast_kernels.cuh): ARITH = A_FAST (B200D_FAST) or A_HYBRID (plane sweep, parity results)
+template <int K, int MODE, int ARITH>
+int launch_sep(const NccArgs &a, cudaStream_t st) {
+    static std::atomic<uint64_t> configured{0};
+    TRY(ensure_smem(ncc_sep_kernel<K, MODE, ARITH>, configured, FGeo<K>::smem_bytes));
+    ProfScope prof((ARITH == A_FAST ? 10000 : 20000) + MODE * 100 + K, st);
+    const dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, 1);
+    ncc_sep_kernel<K, MODE, ARITH><<<grid, NT, FGeo<K>::smem_bytes, st>>>(a);
+    return cuda_check(cudaGetLastError(), "ncc_sep_kernel launch");
+}
+
+template <int MODE, int ARITH>
+int launch_sep_k(int patch, const NccArgs &a, cudaStream_t st) {
+    switch (patch) {
+        case 3: return launch_sep<3, MODE, ARITH>(a, st);
+        case 5: return launch_sep<5, MODE, ARITH>(a, st);
+        case 7: return launch_sep<7, MODE, ARITH>(a, st);
+        case 9: return launch_sep<9, MODE, ARITH>(a, st);
+        case 11: return launch_sep<11, MODE, ARITH>(a, st);
+        case 13: return launch_sep<13, MODE, ARITH>(a, st);
+        default: return fail(B200D_ERR_ARG, "unsupported patch size (odd 3..13)");
+    }
+}
+
 template <int CAND, int BOUNDS>
 int launch_sample(const SampleArgs &a, cudaStream_t st) {
     ProfScope prof(2000 + CAND * 10 + BOUNDS, st);
@@ -201,6 +246,67 @@ int launch_sample(const SampleArgs &a, cudaStream_t st) {
     }
     return cuda_check(cudaGetLastError(), "sample_kernel launch");
 }
+
+// ---- one cost evaluation = sampling + NCC, in the arithmetic the caller chose.
+// B200D_FAST composes the reprojection per source on the host, in double:
+//   q = R_s (R_r^T (Kinv [x,y,1] d - t_r)) + t_s = d (R_s R_r^T Kinv) [x,y,1] + (t_s - R_s R_r^T t_r)
+struct Evaluator {
+    int arith = B200D_PARITY, patch = 0;
+    cudaStream_t st = nullptr;
+    SampleArgs s;
+    NccArgs a;
+    FastCams fc;
+
+    void compose_fast() {
+        const b200d_cams &c = s.cams;
+        fc.n_src = c.n_src;
+        for (int i = 0; i < 6; ++i) fc.K[i] = c.K[i];
+        for (int v = 0; v < c.n_src; ++v) {
+            double A[9], M[9];                                 // A = R_s R_r^T ; M = A Kinv
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) {
+                    double acc = 0;
+                    for (int k = 0; k < 3; ++k) acc += (double)c.R_src[v][i * 3 + k] * (double)c.R_ref[j * 3 + k];
+                    A[i * 3 + j] = acc;
+                }
+            for (int i = 0; i < 3; ++i) {
+                for (int j = 0; j < 3; ++j) {
+                    double acc = 0;
+                    for (int k = 0; k < 3; ++k) acc += A[i * 3 + k] * (double)c.Kinv[k * 3 + j];
+                    M[i * 3 + j] = acc;
+                }
+                double t = (double)c.t_src[v][i];
+                for (int k = 0; k < 3; ++k) t -= A[i * 3 + k] * (double)c.t_ref[k];
+                fc.c[v][i] = (float)t;
+            }
+            for (int i = 0; i < 9; ++i) fc.M[v][i] = (float)M[i];
+        }
+    }
+
+    template <int CAND, int BOUNDS>
+    int sample() {
+        if (arith != B200D_FAST) return launch_sample<CAND, BOUNDS>(s, st);
+        FastSampleArgs f;
+        memset(&f, 0, sizeof(f));
+        for (int i = 0; i < s.cams.n_src; ++i) f.src[i] = s.src[i];
+        f.cams = fc;
+        f.H = s.H; f.W = s.W; f.Wp = s.Wp; f.pad = s.pad; f.map_stride = s.map_stride;
+        f.depth_in = s.depth_in; f.dy = s.dy; f.dx = s.dx;
+        f.depth_min = s.depth_min; f.depth_max = s.depth_max; f.dr = s.dr; f.plane_depth = s.plane_depth;
+        f.rand_u = s.rand_u; f.seed = s.seed; f.view_id = s.view_id; f.eval_id = s.eval_id; f.half = s.half;
+        f.smap = s.smap; f.cand = s.cand; f.valid = s.valid;
+        ProfScope prof(12000 + CAND * 10 + BOUNDS, st);
+        const dim3 grid((f.W + SBX - 1) / SBX, (f.H + SBY - 1) / SBY, 1), block(SBX, SBY, 1);
+        sample_fast_kernel<CAND, BOUNDS><<<grid, block, 0, st>>>(f);
+        return cuda_check(cudaGetLastError(), "sample_fast_kernel launch");
+    }
+
+    template <int MODE>
+    int ncc() {
+        if (arith == B200D_FAST) return launch_sep_k<MODE, A_FAST>(patch, a, st);
+        return launch_ncc_k<MODE>(patch, a, st);
+    }
+};
 
 int check_common(int H, int W, int patch) {
     if (H < 2 || W < 2) return fail(B200D_ERR_ARG, "image must be at least 2x2");
@@ -260,6 +366,29 @@ int stats_impl(const NccArgs &prepared, int H, int W, int patch, float *mean1, f
     n.tm_s[0] = prepared.tm_r;
     n.n_src = 1; n.H = H; n.W = W; n.out = mean1; n.out2 = var1;
     return launch_ncc_k<N_STATS>(patch, n, st);
+}
+
+int check_arith(int arith) {
+    if (arith != B200D_PARITY && arith != B200D_FAST && arith != B200D_PARITY_CHAINS)
+        return fail(B200D_ERR_ARG, "arith must be B200D_PARITY, B200D_FAST or B200D_PARITY_CHAINS");
+    return B200D_OK;
+}
+
+// common set-up of an evaluation context: TMA sources, reference statistics, sampling / NCC argument blocks
+int setup_eval(Evaluator &ev, const float *d_ref, const float *const *d_src, const b200d_cams *cams, int H, int W, int patch,
+               int arith, const Scratch &sc, cudaStream_t st) {
+    ev.arith = (arith == B200D_FAST) ? B200D_FAST : B200D_PARITY;
+    ev.patch = patch;
+    ev.st = st;
+    memset(&ev.a, 0, sizeof(ev.a));
+    TRY(prepare_tma(patch, d_ref, H, W, cams->n_src, sc, ev.a, st));
+    TRY(stats_impl(ev.a, H, W, patch, sc.mean1, sc.var1, st));
+    fill_sample(ev.s, d_src, cams, H, W, patch, sc);
+    if (ev.arith == B200D_FAST) ev.compose_fast();
+    NccArgs &a = ev.a;
+    a.n_src = cams->n_src; a.H = H; a.W = W; a.mean1 = sc.mean1; a.var1 = sc.var1; a.valid = sc.valid; a.cand = sc.cand;
+    a.color = -1;
+    return B200D_OK;
 }
 
 }  // namespace
@@ -335,26 +464,21 @@ int b200d_pm_cost(const float *d_ref, const float *const *d_src, const b200d_cam
                   int W, int patch, int mode, int arith, float *d_out, void *d_scratch, void *stream) {
     TRY(check_common(H, W, patch));
     TRY(check_cams(cams));
+    TRY(check_arith(arith));
     if (!d_ref || !d_src || !d_depth || !d_out || !d_scratch) return fail(B200D_ERR_ARG, "null pointer");
     if (mode != 0 && mode != 1) return fail(B200D_ERR_ARG, "mode must be 0 (cost) or 1 (confidence)");
-    if (arith != B200D_PARITY) return fail(B200D_ERR_UNSUPPORTED, "fast arithmetic not built yet");
     cudaStream_t st = (cudaStream_t)stream;
     Scratch sc(d_scratch, H, W);
-    NccArgs n;
-    memset(&n, 0, sizeof(n));
-    TRY(prepare_tma(patch, d_ref, H, W, cams->n_src, sc, n, st));
-    TRY(stats_impl(n, H, W, patch, sc.mean1, sc.var1, st));
-    SampleArgs s;
-    fill_sample(s, d_src, cams, H, W, patch, sc);
-    s.depth_in = d_depth;
-    n.n_src = cams->n_src; n.H = H; n.W = W; n.mean1 = sc.mean1; n.var1 = sc.var1; n.valid = sc.valid; n.cand = sc.cand;
-    n.out = d_out;
+    Evaluator ev;
+    TRY(setup_eval(ev, d_ref, d_src, cams, H, W, patch, arith, sc, st));
+    ev.s.depth_in = d_depth;
+    ev.a.out = d_out;
     if (mode == 0) {
-        TRY((launch_sample<C_MAP, B_PATCH>(s, st)));
-        return launch_ncc_k<N_COST>(patch, n, st);
+        TRY((ev.sample<C_MAP, B_PATCH>()));
+        return ev.ncc<N_COST>();
     }
-    TRY((launch_sample<C_MAP, B_IMAGE>(s, st)));
-    return launch_ncc_k<N_CONF>(patch, n, st);
+    TRY((ev.sample<C_MAP, B_IMAGE>()));
+    return ev.ncc<N_CONF>();
 }
 
 int b200d_pm_view(const float *d_ref, const float *const *d_src, const b200d_cams *cams, int H, int W,
@@ -363,65 +487,72 @@ int b200d_pm_view(const float *d_ref, const float *const *d_src, const b200d_cam
     if (!prm) return fail(B200D_ERR_ARG, "null params");
     TRY(check_common(H, W, prm->patch));
     TRY(check_cams(cams));
-    if (!d_ref || !d_src || !rng || !d_scratch || !d_depth || !d_normal || !d_conf) return fail(B200D_ERR_ARG, "null pointer");
+    TRY(check_arith(prm->arith));
+    if (!d_ref || !d_src || !rng || !d_scratch || !d_depth || !d_normal) return fail(B200D_ERR_ARG, "null pointer");
     if (prm->iters < 0 || prm->samples < 0) return fail(B200D_ERR_ARG, "negative iteration count");
-    if (prm->arith != B200D_PARITY) return fail(B200D_ERR_UNSUPPORTED, "fast arithmetic not built yet");
+    if (!(prm->depth_min > 0.0) || !std::isfinite(prm->depth_min) || !std::isfinite(prm->depth_max) ||
+        !(prm->depth_max > prm->depth_min))
+        return fail(B200D_ERR_ARG, "need finite 0 < depth_min < depth_max (the initial depths are log-uniform)");
     if (prm->schedule != B200D_SCHEDULE_REFERENCE && prm->schedule != B200D_SCHEDULE_REDBLACK)
         return fail(B200D_ERR_ARG, "unknown propagation schedule");
+    // staged execution (view propagation interleaves the views between iterations): iterations [it_begin, it_end)
+    const int it0 = prm->it_begin, it1 = prm->it_end > 0 ? prm->it_end : prm->iters;
+    const bool do_init = !(prm->stage & B200D_STAGE_NO_INIT), do_conf = !(prm->stage & B200D_STAGE_NO_CONF);
+    if (it0 < 0 || it0 > it1 || it1 > prm->iters) return fail(B200D_ERR_ARG, "need 0 <= it_begin <= it_end <= iters");
+    const bool staged = !do_init || !do_conf || it0 != 0 || it1 != prm->iters;
+    if (staged && !d_best) return fail(B200D_ERR_ARG, "staged execution keeps the best cost in the caller's d_best");
+    if (do_conf && !d_conf) return fail(B200D_ERR_ARG, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n = (size_t)H * W;
     const int patch = prm->patch;
     Scratch sc(d_scratch, H, W);
     // State lives in the caller's output buffers: depth and best are updated in place (only winners
     // write).  Normals ping-pong across the two shifted evaluations of an iteration because a shift
-    // reads the neighbour's normal; two flips per iteration -> the result always ends in d_normal.
+    // reads the neighbour's normal; an even number of flips per iteration -> the state is in d_normal
+    // at every iteration boundary.
     float *depth = d_depth, *best = d_best ? d_best : sc.best;
     float *normal[2] = {d_normal, sc.normal_alt};
 
-    NccArgs a;
-    memset(&a, 0, sizeof(a));
-    TRY(prepare_tma(patch, d_ref, H, W, cams->n_src, sc, a, st));
-    TRY(stats_impl(a, H, W, patch, sc.mean1, sc.var1, st));
+    Evaluator ev;
+    TRY(setup_eval(ev, d_ref, d_src, cams, H, W, patch, prm->arith, sc, st));
+    SampleArgs &s = ev.s;
+    NccArgs &a = ev.a;
 
-    const double ld0 = log(prm->depth_min), ld1 = log(prm->depth_max);
-    {
+    if (do_init) {
+        const double ld0 = log(prm->depth_min), ld1 = log(prm->depth_max);
         ProfScope prof(3000, st);
         pm_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(depth, normal[0], best, n, (float)(ld1 - ld0), (float)ld0,
                                                                     rng->d_init_depth, rng->d_init_normal, rng->seed,
                                                                     rng->view_id);
+        CUDA_TRY(cudaGetLastError());
     }
-    CUDA_TRY(cudaGetLastError());
 
-    SampleArgs s;
-    fill_sample(s, d_src, cams, H, W, patch, sc);
     s.depth_in = depth;
     s.depth_min = (float)prm->depth_min;
     s.depth_max = (float)prm->depth_max;
     s.seed = rng->seed;
     s.view_id = rng->view_id;
-
-    a.n_src = cams->n_src; a.H = H; a.W = W; a.mean1 = sc.mean1; a.var1 = sc.var1; a.valid = sc.valid; a.cand = sc.cand;
     a.depth_in = a.depth_out = depth;
     a.best_in = a.best_out = best;
     a.seed = rng->seed;
     a.view_id = rng->view_id;
 
-    int cn = 0, e = 0;
-    a.color = -1;
+    const int per_it = (prm->schedule == B200D_SCHEDULE_REDBLACK ? 8 : 2) + prm->samples;
+    int cn = 0, e = it0 * per_it;
     // one shifted-neighbour evaluation: candidate = hypothesis of the pixel at (+dy,+dx); `color` restricts who may adopt it
     auto shift_eval = [&](int dy, int dx, int color) -> int {
         s.dy = a.dy = dy;
         s.dx = a.dx = dx;
         a.color = color;
         s.eval_id = a.eval_id = (uint32_t)e;
-        TRY((launch_sample<C_SHIFT, B_PATCH>(s, st)));
+        TRY((ev.sample<C_SHIFT, B_PATCH>()));
         a.normal_in = normal[cn]; a.normal_out = normal[cn ^ 1];
         a.out = d_costs ? d_costs + (size_t)e * n : nullptr;
-        TRY(launch_ncc_k<N_SHIFT>(patch, a, st));
+        TRY(ev.ncc<N_SHIFT>());
         cn ^= 1; ++e;
         return B200D_OK;
     };
-    for (int it = 0; it < prm->iters; ++it) {
+    for (int it = it0; it < it1; ++it) {
         if (prm->schedule == B200D_SCHEDULE_REDBLACK) {
             static const int dirs[4][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}};
             for (int color = 0; color < 2; ++color)
@@ -439,17 +570,62 @@ int b200d_pm_view(const float *d_ref, const float *const *d_src, const b200d_cam
             s.rand_u = rng->d_rand_u ? rng->d_rand_u + k * n : nullptr;
             a.rand_n = rng->d_rand_n ? rng->d_rand_n + k * n * 3 : nullptr;
             s.eval_id = a.eval_id = (uint32_t)e;
-            TRY((launch_sample<C_REFINE, B_PATCH>(s, st)));
+            TRY((ev.sample<C_REFINE, B_PATCH>()));
             a.normal_in = a.normal_out = normal[cn];                            // pixel-local: in place
             a.out = d_costs ? d_costs + (size_t)e * n : nullptr;
-            TRY(launch_ncc_k<N_REFINE>(patch, a, st));
+            TRY(ev.ncc<N_REFINE>());
             ++e;
         }
     }
     if (cn != 0) CUDA_TRY(cudaMemcpyAsync(d_normal, normal[cn], 3 * n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    TRY((launch_sample<C_MAP, B_IMAGE>(s, st)));
+    if (!do_conf) return B200D_OK;
+    TRY((ev.sample<C_MAP, B_IMAGE>()));
     a.out = d_conf;
-    return launch_ncc_k<N_CONF>(patch, a, st);
+    return ev.ncc<N_CONF>();
+}
+
+int b200d_pm_viewprop(const float *d_ref, const float *const *d_src, const b200d_cams *cams, int H, int W,
+                      const b200d_pm_params *prm, const float *const *d_src_depth, const float *const *d_src_normal,
+                      void *d_scratch, float *d_depth, float *d_normal, float *d_best, float *d_costs, void *stream) {
+    if (!prm) return fail(B200D_ERR_ARG, "null params");
+    TRY(check_common(H, W, prm->patch));
+    TRY(check_cams(cams));
+    TRY(check_arith(prm->arith));
+    if (!d_ref || !d_src || !d_src_depth || !d_src_normal || !d_scratch || !d_depth || !d_normal || !d_best)
+        return fail(B200D_ERR_ARG, "null pointer");
+    if (!(prm->depth_min > 0.0) || !(prm->depth_max > prm->depth_min)) return fail(B200D_ERR_ARG, "bad depth range");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)H * W;
+    Scratch sc(d_scratch, H, W);
+    Evaluator ev;
+    TRY(setup_eval(ev, d_ref, d_src, cams, H, W, prm->patch, prm->arith, sc, st));
+    SampleArgs &s = ev.s;
+    NccArgs &a = ev.a;
+    s.depth_in = sc.cand;                     // the candidate map the proposal kernel writes
+    s.cand = nullptr;                         // ... which the sampling kernel therefore must not rewrite
+    a.depth_in = a.depth_out = d_depth;
+    a.best_in = a.best_out = d_best;
+    a.normal_in = sc.normal_alt;              // candidate normals
+    a.normal_out = d_normal;
+    a.allow = sc.allow;
+    for (int v = 0; v < cams->n_src; ++v) {
+        if (!d_src_depth[v] || !d_src_normal[v]) return fail(B200D_ERR_ARG, "null pointer");
+        VpropArgs vp;
+        memset(&vp, 0, sizeof(vp));
+        vp.depth = d_depth; vp.normal = d_normal; vp.depth_src = d_src_depth[v]; vp.normal_src = d_src_normal[v];
+        vp.cams = *cams; vp.s = v; vp.H = H; vp.W = W;
+        vp.depth_min = (float)prm->depth_min; vp.depth_max = (float)prm->depth_max;
+        vp.cand_depth = sc.cand; vp.cand_normal = sc.normal_alt; vp.allow = sc.allow;
+        {
+            ProfScope prof(5100, st);
+            viewprop_cand_kernel<<<dim3((W + 31) / 32, (H + 7) / 8, 1), dim3(32, 8, 1), 0, st>>>(vp);
+        }
+        CUDA_TRY(cudaGetLastError());
+        TRY((ev.sample<C_MAP, B_PATCH>()));
+        a.out = d_costs ? d_costs + (size_t)v * n : nullptr;
+        TRY(ev.ncc<N_VPROP>());
+    }
+    return B200D_OK;
 }
 
 int b200d_plane_sweep(const float *d_ref, const float *const *d_nbr, const b200d_cams *cams, const float *depths_host,
@@ -457,37 +633,54 @@ int b200d_plane_sweep(const float *d_ref, const float *const *d_nbr, const b200d
                       int32_t *d_idx, float *d_ncc, void *d_scratch, void *stream) {
     TRY(check_common(H, W, patch));
     TRY(check_cams(cams));
+    TRY(check_arith(arith));
     if (!d_ref || !d_nbr || !depths_host || !d_depth_map || !d_conf || !d_idx || !d_scratch)
         return fail(B200D_ERR_ARG, "null pointer");
     if (D < 1) return fail(B200D_ERR_ARG, "need at least one depth plane");
     if ((size_t)D > (size_t)H * W) return fail(B200D_ERR_ARG, "more planes than pixels");
-    if (arith != B200D_PARITY) return fail(B200D_ERR_UNSUPPORTED, "fast arithmetic not built yet");
     cudaStream_t st = (cudaStream_t)stream;
     Scratch sc(d_scratch, H, W);
-    NccArgs a;
-    memset(&a, 0, sizeof(a));
-    TRY(prepare_tma(patch, d_ref, H, W, cams->n_src, sc, a, st));
-    TRY(stats_impl(a, H, W, patch, sc.mean1, sc.var1, st));
+    Evaluator ev;
+    TRY(setup_eval(ev, d_ref, d_nbr, cams, H, W, patch, arith, sc, st));
+    SampleArgs &s = ev.s;
+    NccArgs &a = ev.a;
     // plane depths: kernel argument per plane (host) and a device copy for the final gather; the
     // candidate map of the scratch is unused by the sweep and holds the D floats
     float *d_depths = sc.cand;
     CUDA_TRY(cudaMemcpyAsync(d_depths, depths_host, (size_t)D * sizeof(float), cudaMemcpyHostToDevice, st));
-    SampleArgs s;
-    fill_sample(s, d_nbr, cams, H, W, patch, sc);
     s.cand = nullptr;
-    a.n_src = cams->n_src; a.H = H; a.W = W; a.mean1 = sc.mean1; a.var1 = sc.var1; a.valid = sc.valid;
+    a.cand = nullptr;
     a.thresh = thresh; a.n_planes = D; a.depths = d_depths;
-    if (thresh > 1e-3f && thresh < 1e3f) {                    // quick comparison bounds (ncc_kernels.cuh, N_SWEEP)
+    if (thresh > 1e-3f && thresh < 1e3f) {                    // quick comparison bounds (sweep_over, sweep_decide_bounded)
         a.t_lo = (float)((0.999 * thresh) * (0.999 * thresh));
         a.t_hi = (float)((1.001 * thresh) * (1.001 * thresh));
     }
     a.conf = d_conf; a.idx = d_idx; a.depth_map = d_depth_map; a.ncc = d_ncc;
+    // PARITY: separable sums + rigorous bound decide `ncc > thresh`, undecided warps redo the exact chains (bit-exact
+    // counts); PARITY_CHAINS: the exact chains everywhere (A/B reference of the former); the NCC dump needs the values
+    // themselves, hence the chains.
+    const bool hybrid = arith == B200D_PARITY && !d_ncc && a.t_lo > 0.0f;
     for (int d = 0; d < D; ++d) {
         s.plane_depth = depths_host[d];
         a.plane = d;
-        TRY((launch_sample<C_PLANE, B_DEPTH>(s, st)));
-        if (d_ncc) TRY(launch_ncc_k<N_SWEEP_DUMP>(patch, a, st));
+        TRY((ev.sample<C_PLANE, B_DEPTH>()));
+        if (arith == B200D_FAST) TRY((launch_sep_k<N_SWEEP, A_FAST>(patch, a, st)));
+        else if (hybrid) TRY((launch_sep_k<N_SWEEP, A_HYBRID>(patch, a, st)));
+        else if (d_ncc) TRY(launch_ncc_k<N_SWEEP_DUMP>(patch, a, st));
         else TRY(launch_ncc_k<N_SWEEP>(patch, a, st));
+    }
+    return B200D_OK;
+}
+
+int b200d_sweep_fallbacks(uint64_t *count, int reset) {
+    unsigned long long v = 0;
+    if (count) {
+        CUDA_TRY(cudaMemcpyFromSymbol(&v, g_sweep_fallbacks, sizeof(v)));
+        *count = (uint64_t)v;
+    }
+    if (reset) {
+        v = 0;
+        CUDA_TRY(cudaMemcpyToSymbol(g_sweep_fallbacks, &v, sizeof(v)));
     }
     return B200D_OK;
 }
@@ -586,15 +779,50 @@ int b200d_selftest_fast_math(uint64_t n_div, uint64_t *out8, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long *d = nullptr;
     CUDA_TRY(cudaMalloc(&d, 8 * sizeof(unsigned long long)));
-    cudaMemsetAsync(d, 0, 8 * sizeof(unsigned long long), st);
+    cudaError_t e = cudaMemsetAsync(d, 0, 8 * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        return cuda_check(e, "cudaMemsetAsync");
+    }
     selftest_sqrt_kernel<<<148 * 8, 256, 0, st>>>(d + 0, d + 1);
     selftest_div_kernel<<<148 * 8, 256, 0, st>>>(d + 2, d + 3, (unsigned long long)n_div);
     selftest_sample_div_kernel<<<148 * 8, 256, 0, st>>>(d + 4, (unsigned long long)n_div);
-    cudaError_t e = cudaGetLastError();
+    e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(out8, d, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(d);
     return cuda_check(e, "fast-math self-test");
+}
+
+int b200d_measure_fp32_peak(double *tlaneops, void *stream) {
+    if (!tlaneops) return fail(B200D_ERR_ARG, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = sms * 8, block = 256, iters = 20000;
+    float *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, (size_t)grid * block * sizeof(float)));
+    cudaError_t e = cudaMemsetAsync(d, 0, (size_t)grid * block * sizeof(float), st);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    float best = 0.f;
+    for (int rep = 0; rep < 3 && e == cudaSuccess; ++rep) {                 // first repetition warms up
+        cudaEventRecord(e0, st);
+        fma_peak_kernel<<<grid, block, 0, st>>>(d, 0.5f, iters);
+        cudaEventRecord(e1, st);
+        e = cudaEventSynchronize(e1);
+        float ms = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        if (e == cudaSuccess && rep > 0 && (best == 0.f || ms < best)) best = ms;
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_check(e, "fp32 peak measurement");
+    *tlaneops = (double)grid * block * iters * 16.0 / (best * 1e-3) / 1e12;
+    return B200D_OK;
 }
 
 int b200d_prepare_image(const uint8_t *d_bgr, int H, int W, int nh, int nw, const int32_t *d_xi, const int16_t *d_xa,
@@ -611,21 +839,77 @@ int b200d_prepare_image(const uint8_t *d_bgr, int H, int W, int nh, int nw, cons
 }
 
 // Host-side: ASCII PLY in the reference's exact format (src/core/utils.py:8-37): "%.6f %.6f %.6f %d %d %d\n".
-// The reference formats one point per Python iteration; this is a buffered C writer (same bytes).
+// The reference formats one point per Python iteration.  Here blocks of points are formatted in parallel (OpenMP:
+// every thread snprintf's a contiguous run of vertices into its own buffer) and the buffers are written in order, so
+// the file is byte-identical to the sequential writer's.
 int b200d_write_ply_ascii(const char *path, const double *points, const uint8_t *colors, int64_t n) {
     if (!path || n < 0 || (n > 0 && (!points || !colors))) return fail(B200D_ERR_ARG, "bad argument");
     FILE *f = fopen(path, "wb");
     if (!f) return fail(B200D_ERR_ARG, "cannot open output file");
-    std::vector<char> buf(1 << 22);
-    setvbuf(f, buf.data(), _IOFBF, buf.size());
     fprintf(f, "ply\nformat ascii 1.0\nelement vertex %lld\nproperty float x\nproperty float y\nproperty float z\n"
                "property uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n", (long long)n);
-    for (int64_t i = 0; i < n; ++i)
-        fprintf(f, "%.6f %.6f %.6f %d %d %d\n", points[3 * i], points[3 * i + 1], points[3 * i + 2], (int)colors[3 * i],
-                (int)colors[3 * i + 1], (int)colors[3 * i + 2]);
-    const bool bad = ferror(f) != 0;
+    int T = 1;
+#ifdef _OPENMP
+    T = omp_get_max_threads();
+    if (T > 64) T = 64;
+#endif
+    const int64_t BLOCK = 1 << 22;                       // vertices formatted per round (bounds the staging memory)
+    // "%.6f" of a double prints at most 1 + 309 + 1 + 6 characters; coordinates of a cloud are a few digits, so
+    // reserve generously per vertex and let snprintf report the length actually used
+    std::vector<std::vector<char>> bufs((size_t)T);
+    std::vector<size_t> used((size_t)T);
+    bool bad = false;
+    for (int64_t b0 = 0; b0 < n && !bad; b0 += BLOCK) {
+        const int64_t bn = (n - b0 < BLOCK) ? n - b0 : BLOCK;
+        const int64_t per = (bn + T - 1) / T;
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+        for (int t = 0; t < T; ++t) {
+            const int64_t i0 = b0 + (int64_t)t * per, i1 = (i0 + per < b0 + bn) ? i0 + per : b0 + bn;
+            std::vector<char> &buf = bufs[(size_t)t];
+            size_t pos = 0;
+            for (int64_t i = i0; i < i1; ++i) {
+                if (buf.size() < pos + 1024) buf.resize(buf.size() * 2 + (1 << 16));
+                int w = snprintf(buf.data() + pos, buf.size() - pos, "%.6f %.6f %.6f %d %d %d\n", points[3 * i],
+                                 points[3 * i + 1], points[3 * i + 2], (int)colors[3 * i], (int)colors[3 * i + 1],
+                                 (int)colors[3 * i + 2]);
+                if (w < 0) w = 0;
+                if ((size_t)w >= buf.size() - pos) {                     // astronomically large coordinate: grow and redo
+                    buf.resize(buf.size() * 2 + (size_t)w + 1024);
+                    w = snprintf(buf.data() + pos, buf.size() - pos, "%.6f %.6f %.6f %d %d %d\n", points[3 * i],
+                                 points[3 * i + 1], points[3 * i + 2], (int)colors[3 * i], (int)colors[3 * i + 1],
+                                 (int)colors[3 * i + 2]);
+                }
+                pos += (size_t)w;
+            }
+            used[(size_t)t] = pos;
+        }
+        for (int t = 0; t < T && !bad; ++t)
+            if (used[(size_t)t] && fwrite(bufs[(size_t)t].data(), 1, used[(size_t)t], f) != used[(size_t)t]) bad = true;
+    }
+    bad = bad || ferror(f) != 0;
     if (fclose(f) != 0 || bad) return fail(B200D_ERR_ARG, "write failed");
     return B200D_OK;
+}
+
+// count-only pass of the fusion mask (same mask as b200d_mask_backproject): lets a caller size one exact output buffer
+// for many views with a single host synchronisation
+int b200d_mask_count(const float *d_depth, const float *d_conf, int H, int W, float min_conf, int mode, int64_t *d_count,
+                     void *d_scratch, void *stream) {
+    if (H < 1 || W < 1) return fail(B200D_ERR_ARG, "empty image");
+    if (!d_depth || !d_conf || !d_count || !d_scratch) return fail(B200D_ERR_ARG, "null pointer");
+    if (mode != 0 && mode != 1) return fail(B200D_ERR_ARG, "mode must be 0 (PatchMatch) or 1 (plane sweep)");
+    FuseArgs a;
+    memset(&a, 0, sizeof(a));
+    a.depth = d_depth; a.conf = d_conf; a.H = H; a.W = W; a.min_conf = min_conf; a.mode = mode; a.count = d_count;
+    const size_t chunks = ((size_t)H * W + FUSE_CHUNK - 1) / FUSE_CHUNK;
+    a.n_chunks = (int)chunks;
+    a.chunk_counts = (uint32_t *)d_scratch;
+    a.chunk_offsets = (int64_t *)((char *)d_scratch + align256(chunks * sizeof(uint32_t)));
+    cudaStream_t st = (cudaStream_t)stream;
+    ProfScope prof(4100, st);
+    fuse_count_kernel<<<(unsigned)chunks, FUSE_NT, 0, st>>>(a);
+    fuse_scan_kernel<<<1, 1024, 0, st>>>(a);
+    return cuda_check(cudaGetLastError(), "fuse count kernels launch");
 }
 
 int b200d_mask_backproject(const float *d_depth, const float *d_conf, const uint8_t *d_bgr, int H, int W,

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT = os.path.join(HERE, 'libb200dense.so')
 SRCS = ['b200dense.cu']
-DEPS = SRCS + ['device_math.cuh', 'sample_kernels.cuh', 'ncc_kernels.cuh', 'fuse_kernels.cuh', 'geo_kernels.cuh', 'prep_kernels.cuh', 'knn_kernels.cuh',
+DEPS = SRCS + ['device_math.cuh', 'sample_kernels.cuh', 'ncc_kernels.cuh', 'fast_kernels.cuh', 'diag_kernels.cuh', 'fuse_kernels.cuh', 'geo_kernels.cuh', 'prep_kernels.cuh', 'knn_kernels.cuh',
                os.path.join(ROOT, 'include', 'b200dense.h')]
 
 
@@ -40,9 +40,9 @@ def build(force=False, verbose=False, out=None, defines=()):
         OUT_ = out
     else:
         OUT_ = OUT
-    cmd = [nvcc(), *[f'-D{d}' for d in defines], '-shared', '-Xcompiler', '-fPIC,-fvisibility=hidden', '-std=c++17', '-O3', '-lineinfo',
+    cmd = [nvcc(), *[f'-D{d}' for d in defines], '-shared', '-Xcompiler', '-fPIC,-fvisibility=hidden,-fopenmp', '-std=c++17', '-O3', '-lineinfo',
            '-gencode', 'arch=compute_100a,code=sm_100a', '-fmad=false', '-ccbin', '/usr/bin/g++',
-           '-I', os.path.join(ROOT, 'include'), '-I', HERE, '-o', OUT_] + [os.path.join(HERE, s) for s in SRCS]
+           '-I', os.path.join(ROOT, 'include'), '-I', HERE, '-o', OUT_] + [os.path.join(HERE, s) for s in SRCS] + ['-lgomp']
     if verbose:
         cmd.insert(1, '-Xptxas=-v')
     subprocess.check_call(cmd)

@@ -1,0 +1,465 @@
+// fast_kernels.cuh -- separable window sums: the B200D_FAST arithmetic mode and the error-bounded plane sweep.
+//
+// The parity kernels (ncc_kernels.cuh) spend 3*K*K FMAs per (pixel, source) because every output of the reference's
+// conv2d is its own rounding chain.  Mathematically the three window sums are separable.  This file holds the
+// separable formulation, used in two ways:
+//
+//   ARITH = A_FAST    opt-in B200D_FAST mode (NOT bit-exact, not the graded path): composed reprojection
+//                     q = d * (M [x,y,1]) + c in sample_fast_kernel, direct bilinear lookup, separable sums, MUFU
+//                     reciprocal / rsqrt in the NCC.  Its deviation from the oracle is measured, not hidden
+//                     (tests/test_gpu_fast.py, bench.py --arith fast).
+//   ARITH = A_HYBRID  plane sweep in PARITY mode.  The sweep only ever uses the NCC through `ncc > thresh`
+//                     (dense_stereo.py:303), so the comparison is first decided from the separable sums together
+//                     with a rigorous bound on their distance to the reference's chains (derivation at
+//                     sweep_decide_bounded); the few outputs the bound cannot decide (~2e-4) make their warp redo the
+//                     window with the exact row-major chains (box_sums) from the tile still in shared memory.  Counts
+//                     and arg-max stay bit-identical to the oracle; the sampling kernel is the parity one.
+//
+// Window sums, per CTA tile (TW x TH outputs, window (TW+K-1) x (TH+K-1) in shared memory via TMA as before):
+//   H phase  every (window row, group of 4 output columns): products s*s, r*s, then the K-tap horizontal sums of
+//            s, s*s, r*s for the 4 outputs (shared partial sums, additions only) -> h[3][RH][TW] in shared memory
+//   V phase  every thread: K+1 rows of h for its 4x2 outputs, vertical sums, scale by 1/K^2
+// ~27 lane-ops per (pixel, source) at K=7 instead of 167; shared-memory bandwidth, not the FMA pipe, bounds it.
+#pragma once
+#include "ncc_kernels.cuh"
+#include "sample_kernels.cuh"
+
+namespace b200d {
+
+enum FastArith { A_FAST = 0, A_HYBRID = 1 };
+
+// ------------------------------------------------------------------------------------------------ sampling (A_FAST)
+struct FastCams {
+    float M[B200D_MAX_SRC][9];               // R_s R_r^T K^-1
+    float c[B200D_MAX_SRC][3];               // t_s - R_s R_r^T t_r
+    float K[6];                              // first two rows of K
+    int n_src;
+};
+
+struct FastSampleArgs {
+    const float *src[B200D_MAX_SRC];
+    FastCams cams;
+    int H, W, Wp, pad;
+    size_t map_stride;
+    const float *depth_in;
+    int dy, dx;
+    float depth_min, depth_max, dr, plane_depth;
+    const float *rand_u;
+    uint64_t seed;
+    uint32_t view_id, eval_id;
+    int half;
+    float *smap, *cand;
+    uint8_t *valid;
+};
+
+template <int CAND, int BOUNDS>
+__global__ void __launch_bounds__(SBX *SBY) sample_fast_kernel(const __grid_constant__ FastSampleArgs a) {
+    const int x = blockIdx.x * SBX + threadIdx.x, y = blockIdx.y * SBY + threadIdx.y;
+    if (x >= a.W || y >= a.H) return;
+    const int W = a.W, H = a.H;
+    const size_t g = (size_t)y * W + x;
+    float cd;
+    if (CAND == C_MAP) {
+        cd = __ldg(a.depth_in + g);
+    } else if (CAND == C_SHIFT) {
+        const int nx = x + a.dx, ny = y + a.dy;
+        cd = (nx >= 0 && nx < W && ny >= 0 && ny < H) ? __ldg(a.depth_in + (size_t)ny * W + nx) : a.depth_min;
+    } else if (CAND == C_REFINE) {
+        float u;
+        if (a.rand_u) {
+            u = __ldg(a.rand_u + g);
+        } else {
+            const uint4 rn = philox4x32_10(make_uint4((uint32_t)g, a.eval_id, a.view_id, 0u),
+                                           make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+            u = u01(rn.x);
+        }
+        cd = fminf(fmaxf(fmaf(fmaf(u, 2.0f, -1.0f), a.dr, __ldg(a.depth_in + g)), a.depth_min), a.depth_max);
+    } else {
+        cd = a.plane_depth;
+    }
+    const float fxp = (float)x, fyp = (float)y;
+    const float lo = (BOUNDS == B_PATCH) ? (float)a.half : 0.0f;
+    const float hix = (BOUNDS == B_PATCH) ? (float)(W - a.half) : (float)W;
+    const float hiy = (BOUNDS == B_PATCH) ? (float)(H - a.half) : (float)H;
+    const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
+    unsigned vmask = 0;
+    float *out = a.smap + (size_t)y * a.Wp + x + a.pad;
+    const int S = a.cams.n_src;
+#pragma unroll 2
+    for (int s = 0; s < S; ++s) {
+        const float *M = a.cams.M[s], *c = a.cams.c[s], *Kc = a.cams.K;
+        const float qx = fmaf(cd, fmaf(M[0], fxp, fmaf(M[1], fyp, M[2])), c[0]);
+        const float qy = fmaf(cd, fmaf(M[3], fxp, fmaf(M[4], fyp, M[5])), c[1]);
+        const float qz = fmaf(cd, fmaf(M[6], fxp, fmaf(M[7], fyp, M[8])), c[2]);
+        const float iz = __fdividef(1.0f, qz + 1e-8f);
+        const float px = qx * iz, py = qy * iz;
+        const float u = fmaf(Kc[0], px, fmaf(Kc[1], py, Kc[2])), v = fmaf(Kc[3], px, fmaf(Kc[4], py, Kc[5]));
+        bool ok = qz > 0.1f;
+        if (BOUNDS != B_DEPTH) ok = ok & (u >= lo) & (u < hix) & (v >= lo) & (v < hiy);
+        vmask |= (unsigned)ok << s;
+        const float x0 = floorf(u), y0 = floorf(v);
+        const float wx = u - x0, wy = v - y0;
+        const bool x0in = (x0 >= 0.0f) & (x0 <= wm1), x1in = (x0 >= -1.0f) & (x0 <= wm1 - 1.0f);
+        const bool y0in = (y0 >= 0.0f) & (y0 <= hm1), y1in = (y0 >= -1.0f) & (y0 <= hm1 - 1.0f);
+        const float *p0 = a.src[s] + (int)y0 * W + (int)x0;          // only dereferenced for taps inside the image
+        const float vnw = (x0in & y0in) ? __ldg(p0) : 0.0f;
+        const float vne = (x1in & y0in) ? __ldg(p0 + 1) : 0.0f;
+        const float vsw = (x0in & y1in) ? __ldg(p0 + W) : 0.0f;
+        const float vse = (x1in & y1in) ? __ldg(p0 + W + 1) : 0.0f;
+        const float top = fmaf(wx, vne - vnw, vnw), bot = fmaf(wx, vse - vsw, vsw);
+        out[(size_t)s * a.map_stride] = fmaf(wy, bot - top, top);
+    }
+    if (a.cand) a.cand[g] = cd;
+    a.valid[g] = (uint8_t)vmask;
+}
+
+// ------------------------------------------------------------------------------------------------ separable sums
+template <int K>
+struct FGeo {
+    using G = Geo<K>;
+    static constexpr int HR = G::RH;                                         // rows of horizontal sums
+    static constexpr int HCH = HR * TW;                                      // floats per channel of h
+    static constexpr uint32_t h_bytes = 3u * HCH * sizeof(float);
+    static constexpr size_t smem_bytes = 3 * (size_t)G::buf_bytes + h_bytes + 64;   // r + 2 stages + h + barriers
+};
+
+// K-tap window sums of 4 adjacent outputs from the K+3 values v[0..K+2]: out[p] = v[p] + ... + v[p+K-1].
+// Additions only (no sliding subtraction): every result is a plain sum of its K terms, longest path K-2 additions.
+template <int K, int NL>
+__device__ __forceinline__ float4 hsum4(const float (&v)[NL]) {
+    static_assert(NL >= K + 3, "window row too short");
+    float4 o;
+    if constexpr (K == 3) {
+        const float t12 = v[1] + v[2], t34 = v[3] + v[4];
+        o.x = v[0] + t12; o.y = t12 + v[3]; o.z = v[2] + t34; o.w = t34 + v[5];
+    } else {
+        float common = v[3];
+#pragma unroll
+        for (int j = 4; j < K; ++j) common += v[j];                           // v[3..K-1] is shared by all four
+        const float t12 = v[1] + v[2], tk = v[K] + v[K + 1];
+        o.x = common + (v[0] + t12);
+        o.y = common + (t12 + v[K]);
+        o.z = common + (v[2] + tk);
+        o.w = common + (tk + v[K + 2]);
+    }
+    return o;
+}
+
+// H phase: all threads of the CTA; h[ch][row][col], ch 0 = s, 1 = s*s, 2 = r*s.
+template <int K>
+__device__ __forceinline__ void hphase(const float *__restrict__ s_s, const float *__restrict__ s_r, float *__restrict__ s_h,
+                                       int tid) {
+    using G = Geo<K>;
+    constexpr int NL = G::NL, RWP = G::RWP, HR = FGeo<K>::HR, HCH = FGeo<K>::HCH;
+#pragma unroll
+    for (int i0 = 0; i0 < HR * NTX; i0 += NT) {
+        const int i = i0 + tid;
+        if (i >= HR * NTX) continue;                                         // ragged last round
+        const int row = i / NTX, grp = i % NTX;
+        float sv[NL], rv[NL], s2[NL], rs[NL];
+        load_row<NL>(s_s + row * RWP + grp * PX, sv);
+        load_row<NL>(s_r + row * RWP + grp * PX, rv);
+#pragma unroll
+        for (int j = 0; j < NL; ++j) {
+            s2[j] = sv[j] * sv[j];                                           // same products as the exact chains
+            rs[j] = rv[j] * sv[j];
+        }
+        float4 *o = reinterpret_cast<float4 *>(s_h + row * TW + grp * PX);
+        o[0] = hsum4<K, NL>(sv);
+        o[HCH / 4] = hsum4<K, NL>(s2);
+        o[2 * (HCH / 4)] = hsum4<K, NL>(rs);
+    }
+}
+
+// V phase: K+1 rows of one channel for this thread's PX x QY outputs; result scaled by 1/K^2.
+template <int K>
+__device__ __forceinline__ void vphase(const float *__restrict__ h, int tx, int ty, float (&o)[QY][PX]) {
+    static_assert(QY == 2 && PX == 4, "thread tile is 4 x 2");
+    constexpr float w = 1.0f / (float)(K * K);
+    constexpr int RS = TW / 4;
+    const float4 *p = reinterpret_cast<const float4 *>(h + (ty * QY) * TW + tx * PX);
+    float4 c = p[RS];
+#pragma unroll
+    for (int i = 2; i < K; ++i) {
+        const float4 t = p[i * RS];
+        c.x += t.x; c.y += t.y; c.z += t.z; c.w += t.w;                      // rows 1..K-1 are shared by both outputs
+    }
+    const float4 a0 = p[0], ak = p[K * RS];
+    o[0][0] = (c.x + a0.x) * w; o[0][1] = (c.y + a0.y) * w; o[0][2] = (c.z + a0.z) * w; o[0][3] = (c.w + a0.w) * w;
+    o[1][0] = (c.x + ak.x) * w; o[1][1] = (c.y + ak.y) * w; o[1][2] = (c.z + ak.z) * w; o[1][3] = (c.w + ak.w) * w;
+}
+
+// ------------------------------------------------------------------------------------------------ bounded decision
+// Decide `ncc > thresh` for the reference's NCC  ncc = cov / sqrt(var1*var2 + 1e-8)  (dense_stereo.py:337-345) from the
+// separable sums m2~, a2~ = box(s*s)~, ar~ = box(r*s)~, without knowing the reference's own (chain) values m2, a2, ar.
+//
+// Notation: u = 2^-24, w = fl(1/K^2) (same constant in both paths), gamma_n = n u / (1 - n u).
+//   chain   acc = fma(x_i, w, acc), K^2 steps:      |chain - w sum x_i|  <= gamma_{K^2} * w sum |x_i|
+//   fast    (tree sum of the same terms) * w:       |fast  - w sum x_i|  <= gamma_{2K}  * w sum |x_i|
+//   (the terms x_i are identical in both paths: s_i, fl(s_i*s_i), fl(r_i*s_i))
+// so with C = (K^2 + 2K + 8) u * 1.5 (50 % safety on top of the slack of 8 u):
+//   |m2 - m2~| <= es  = C/2 (1 + a2~)            since  mean|s| <= (1 + mean s^2)/2, mean s^2 <= a2~ (1 + gamma)
+//   |a2 - a2~| <= ess = C a2~
+//   |ar - ar~| <= ers = C/2 (Br + a2~)           since  |r s| <= (r^2 + s^2)/2,  Br >= mean r^2  (Br = (var1 + m1^2)(1+1e-4))
+// and through  var2 = fl(a2 - fl(m2 m2)),  cov = fl(ar - fl(m1 m2)),  x = fl(fl(var1 var2) + 1e-8):
+//   |var2 - var2~| <= ev = ess + (2|m2~| + es) es + 4.1u (a2~ + m2~^2)
+//   |cov  - cov~ | <= ec = ers + |m1| es + 4.1u (|ar~| + |m1 m2~|)
+//   |x    - x~   | <= ex = |var1| ev + 4.1u (|x~| + 2e-8)
+// The reference's comparison is then implied by the quick test of the exact kernel (sweep_over: margins 0.1 % on the
+// threshold, four orders above the rounding of sqrt / division) evaluated at the worst corner of the box
+// [cov~ -+ ec] x [x~ -+ ex].  NaN anywhere fails every comparison -> undecided -> exact path.
+// Returns 1 = over, 0 = not over, 2 = undecided.
+template <int K>
+__device__ __forceinline__ int sweep_decide_bounded(float m2, float a2, float ar, float m1, float v1, float br, float t_lo,
+                                                    float t_hi) {
+    constexpr float U = 5.9604645e-8f;
+    constexpr float C = (float)(K * K + 2 * K + 8) * U * 1.5f;
+    constexpr float U4 = 4.1f * U;
+    const float m2sq = m2 * m2, m1m2 = m1 * m2;
+    const float v2 = a2 - m2sq;
+    const float cov = ar - m1m2;
+    const float x = v1 * v2 + 1e-8f;
+    const float es = (0.5f * C) * (a2 + 1.0f);
+    const float ess = C * a2;
+    const float ers = (0.5f * C) * (br + a2);
+    const float ev = fmaf(U4, a2 + m2sq, fmaf(fmaf(2.0f, fabsf(m2), es), es, ess));
+    const float ec = fmaf(U4, fabsf(ar) + fabsf(m1m2), fmaf(fabsf(m1), es, ers));
+    const float ex = fmaf(fabsf(v1), ev, U4 * (fabsf(x) + 2e-8f));
+    const float c_lo = cov - ec, c_hi = cov + ec, x_lo = x - ex, x_hi = x + ex;
+    const bool sure_t = (c_lo > 0.0f) & (x_lo > 0.0f) & (c_lo * c_lo > x_hi * t_hi);
+    const bool sure_f = (c_hi <= 0.0f) | ((x_lo > 0.0f) & (c_hi * c_hi < x_lo * t_lo));
+    return sure_t ? 1 : (sure_f ? 0 : 2);
+}
+
+// hybrid sweep: number of (warp, neighbour) evaluations redone with the exact chains (b200d_sweep_fallbacks); the
+// denominator -- live warps x neighbours x planes -- is known on the host, so the common path carries no atomic
+__device__ unsigned long long g_sweep_fallbacks;
+
+// ------------------------------------------------------------------------------------------------ NCC kernel
+// Same tile, TMA pipeline and epilogue rules as ncc_kernel.  MODE: N_COST, N_CONF, N_SHIFT, N_REFINE, N_VPROP, N_SWEEP
+// for A_FAST; N_SWEEP only for A_HYBRID.
+#ifndef B200D_SEP_MIN_BLOCKS
+#define B200D_SEP_MIN_BLOCKS 3
+#endif
+template <int K, int MODE, int ARITH>
+__global__ void __launch_bounds__(NT, B200D_SEP_MIN_BLOCKS) ncc_sep_kernel(const __grid_constant__ NccArgs a) {
+    using G = Geo<K>;
+    using FG = FGeo<K>;
+    constexpr int HALF = G::HALF;
+    static_assert(ARITH == A_FAST || MODE == N_SWEEP, "the bounded decision exists for the plane sweep only");
+    extern __shared__ __align__(128) unsigned char sm[];
+    constexpr int BUF = G::buf_bytes / sizeof(float);
+    float *s_r = reinterpret_cast<float *>(sm);
+    float *s_h = reinterpret_cast<float *>(sm + 3 * G::buf_bytes);           // [3][HR][TW]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sm + 3 * G::buf_bytes + FG::h_bytes);   // [0],[1]: stages ; [2]: reference
+
+    const int tid = threadIdx.x;
+    const int tx = tid % NTX, ty = tid / NTX;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int H = a.H, W = a.W, S = a.n_src;
+    const int cx = x0 - HALF + G::PAD, cy = y0 - HALF;
+
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_init(&bar[2], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar[2], G::tile_bytes);
+        tma_load_2d(s_r, &a.tm_r, &bar[2], cx, cy);
+        mbar_expect_tx(&bar[0], G::tile_bytes);
+        tma_load_2d(s_r + BUF, &a.tm_s[0], &bar[0], cx, cy);
+        if (S > 1) {
+            mbar_expect_tx(&bar[1], G::tile_bytes);
+            tma_load_2d(s_r + 2 * BUF, &a.tm_s[1], &bar[1], cx, cy);
+        }
+    }
+
+    float m1[QY][PX], v1[QY][PX], br[QY][PX], total[QY][PX];
+    unsigned vb[QY], cnt = 0;
+#pragma unroll
+    for (int q = 0; q < QY; ++q) {
+        vb[q] = 0;
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+            const int gx = x0 + tx * PX + p, gy = y0 + ty * QY + q;
+            const bool in = gx < W && gy < H;
+            const size_t g = (size_t)gy * W + gx;
+            m1[q][p] = in ? __ldg(a.mean1 + g) : 0.0f;
+            v1[q][p] = in ? __ldg(a.var1 + g) : 0.0f;
+            // validity bits of outputs outside the image stay 0: they never count and never need the exact path
+            vb[q] |= (in ? (unsigned)__ldg(a.valid + g) : 0u) << (8 * p);
+            br[q][p] = (v1[q][p] + m1[q][p] * m1[q][p]) * 1.0001f;
+            total[q][p] = 0.0f;
+        }
+    }
+
+    const int lane = tid & 31;
+    const bool warp_live = y0 + (tid / 32) * (32 / NTX) * QY < H;
+    mbar_wait(&bar[2], 0);
+    for (int s = 0; s < S; ++s) {
+        const int st = s & 1;
+        mbar_wait(&bar[st], (s >> 1) & 1);
+        const float *sb = s_r + (1 + st) * BUF;
+        hphase<K>(sb, s_r, s_h, tid);
+        __syncthreads();                                   // h complete
+        float as[QY][PX], ass[QY][PX], ars[QY][PX];
+        if (warp_live) {
+            vphase<K>(s_h, tx, ty, as);
+            vphase<K>(s_h + FG::HCH, tx, ty, ass);
+            vphase<K>(s_h + 2 * FG::HCH, tx, ty, ars);
+        }
+        if (ARITH == A_HYBRID) {
+            // ---- plane sweep, parity results: bounded decision, exact redo of the warps that hold an undecided output
+            unsigned over = 0, und = 0;
+            if (warp_live) {
+#pragma unroll
+                for (int q = 0; q < QY; ++q)
+#pragma unroll
+                    for (int p = 0; p < PX; ++p) {
+                        const bool valid = (vb[q] >> (8 * p + s)) & 1u;
+                        const int dcs = (a.t_lo > 0.0f) ? sweep_decide_bounded<K>(as[q][p], ass[q][p], ars[q][p], m1[q][p],
+                                                                                  v1[q][p], br[q][p], a.t_lo, a.t_hi)
+                                                        : 2;
+                        over |= (dcs == 1 ? 1u : 0u) << (q * PX + p);
+                        und |= ((dcs == 2) & valid ? 1u : 0u) << (q * PX + p);
+                    }
+                if (__any_sync(0xffffffffu, und != 0)) {
+                    box_sums<K>(sb, s_r, tx, ty, as, ass, ars);               // the reference's chains, tile still resident
+                    over = 0;
+#pragma unroll
+                    for (int q = 0; q < QY; ++q)
+#pragma unroll
+                        for (int p = 0; p < PX; ++p) {
+                            const float m2 = as[q][p];
+                            const float v2 = sub(ass[q][p], mul(m2, m2));
+                            const float cov = sub(ars[q][p], mul(m1[q][p], m2));
+                            const float x = add(mul(v1[q][p], v2), 1e-8f);
+                            over |= (sweep_over(cov, x, a.thresh, a.t_lo, a.t_hi) ? 1u : 0u) << (q * PX + p);
+                        }
+                    if (lane == 0) atomicAdd(&g_sweep_fallbacks, 1ull);
+                }
+#pragma unroll
+                for (int q = 0; q < QY; ++q)
+#pragma unroll
+                    for (int p = 0; p < PX; ++p) {
+                        const bool valid = (vb[q] >> (8 * p + s)) & 1u;
+                        if (((over >> (q * PX + p)) & 1u) && valid) total[q][p] = add(total[q][p], 1.0f);   // :303-304
+                    }
+            }
+        } else if (warp_live) {
+            // ---- B200D_FAST: same formulas, MUFU reciprocal / rsqrt, no rounding discipline
+#pragma unroll
+            for (int q = 0; q < QY; ++q)
+#pragma unroll
+                for (int p = 0; p < PX; ++p) {
+                    const float m2 = as[q][p];
+                    const float v2 = ass[q][p] - m2 * m2;
+                    const float cov = ars[q][p] - m1[q][p] * m2;
+                    const bool valid = (vb[q] >> (8 * p + s)) & 1u;
+                    if (MODE == N_SWEEP) {
+                        const float ncc = cov * rsqrtf(v1[q][p] * v2 + 1e-8f);
+                        if (a.ncc) {
+                            const int gx = x0 + tx * PX + p, gy = y0 + ty * QY + q;
+                            if (gx < W && gy < H) a.ncc[(((size_t)a.plane * S + s) * H + gy) * W + gx] = ncc;
+                        }
+                        if ((ncc > a.thresh) && valid) total[q][p] += 1.0f;
+                    } else {
+                        const float ncc = __fdividef(cov, sqrtf(v1[q][p] * v2) + 1e-8f);
+                        if (MODE == N_CONF) {
+                            if (valid && (ncc > 0.6f)) total[q][p] += 1.0f;
+                        } else {
+                            total[q][p] += valid ? 1.0f - ncc : 0.0f;
+                            cnt += valid ? (1u << (4 * (q * PX + p))) : 0u;
+                        }
+                    }
+                }
+        }
+        __syncthreads();                                   // h and stage st are free again
+        if (tid == 0 && s + 2 < S) {
+            mbar_expect_tx(&bar[st], G::tile_bytes);
+            tma_load_2d(s_r + (1 + st) * BUF, &a.tm_s[s + 2], &bar[st], cx, cy);
+        }
+    }
+
+    // ---- epilogue (same rules as ncc_kernel)
+#pragma unroll
+    for (int q = 0; q < QY; ++q)
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+            const int gx = x0 + tx * PX + p, gy = y0 + ty * QY + q;
+            if (gx >= W || gy >= H) continue;
+            const size_t g = (size_t)gy * W + gx;
+            if (MODE == N_CONF) {
+                a.out[g] = total[q][p];
+                continue;
+            }
+            if (MODE == N_SWEEP) {
+                // running first-max over planes (torch.max(dim=0), dense_stereo.py:307)
+                const float prev = (a.plane == 0) ? -1.0f : a.conf[g];
+                int bi = (a.plane == 0) ? 0 : a.idx[g];
+                float bc = prev;
+                if (total[q][p] > prev) { bc = total[q][p]; bi = a.plane; }
+                if (bc != prev) { a.conf[g] = bc; a.idx[g] = bi; }
+                if (a.plane == a.n_planes - 1) a.depth_map[g] = __ldg(a.depths + bi);          // :310
+                continue;
+            }
+            const float cntf = (float)((cnt >> (4 * (q * PX + p))) & 15u);
+            const float cost = (cntf >= 2.0f) ? __fdividef(total[q][p], cntf) : __int_as_float(0x7f800000);
+            if (a.out) a.out[g] = cost;
+            if (MODE == N_COST) continue;
+            const float best = a.best_in[g];
+            bool better = cost < best;
+            if (MODE == N_SHIFT && a.color >= 0) better = better && ((gx + gy) & 1) == a.color;
+            if (MODE == N_VPROP) better = better && (__ldg(a.allow + g) != 0);
+            if (better) a.depth_out[g] = __ldg(a.cand + g);
+            else if (a.depth_out != a.depth_in) a.depth_out[g] = a.depth_in[g];
+            if (better || a.best_out != a.best_in) a.best_out[g] = better ? cost : best;
+            if (MODE == N_VPROP) {
+                if (better) {
+                    const float *np = a.normal_in + 3 * g;
+                    float *no = a.normal_out + 3 * g;
+                    no[0] = np[0]; no[1] = np[1]; no[2] = np[2];
+                }
+                continue;
+            }
+            float n0, n1, n2;
+            if (better) {
+                if (MODE == N_SHIFT) {
+                    const int nx = gx + a.dx, ny = gy + a.dy;
+                    if (nx >= 0 && nx < W && ny >= 0 && ny < H) {
+                        const float *np = a.normal_in + 3 * ((size_t)ny * W + nx);
+                        n0 = np[0]; n1 = np[1]; n2 = np[2];
+                    } else {
+                        n0 = n1 = n2 = 0.0f;
+                    }
+                } else {
+                    float r0, r1, r2;
+                    if (a.rand_n) {
+                        const float *rp = a.rand_n + 3 * g;
+                        r0 = __ldg(rp); r1 = __ldg(rp + 1); r2 = __ldg(rp + 2);
+                    } else {
+                        const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+                        const uint4 ra = philox4x32_10(make_uint4((uint32_t)g, a.eval_id, a.view_id, 1u), key);
+                        gauss2(ra.x, ra.y, r0, r1);
+                        r2 = gauss(ra.z, ra.w);
+                    }
+                    const float *np = a.normal_in + 3 * g;
+                    const float c0 = fmaf(r0, a.nr, np[0]), c1 = fmaf(r1, a.nr, np[1]), c2 = fmaf(r2, a.nr, np[2]);
+                    const float in_ = rsqrtf(fmaxf(fmaf(c0, c0, fmaf(c1, c1, c2 * c2)), 1e-24f));
+                    n0 = c0 * in_; n1 = c1 * in_; n2 = c2 * in_;
+                }
+            } else if (a.normal_out != a.normal_in) {
+                const float *np = a.normal_in + 3 * g;
+                n0 = np[0]; n1 = np[1]; n2 = np[2];
+            }
+            if (better || a.normal_out != a.normal_in) {
+                float *no = a.normal_out + 3 * g;
+                no[0] = n0; no[1] = n1; no[2] = n2;
+            }
+        }
+}
+
+}  // namespace b200d

@@ -35,7 +35,8 @@ constexpr int PX = 4, QY = 2;                                  // outputs per th
 constexpr int NTX = TW / PX, NTY = TH / QY, NT = NTX * NTY;    // 16 x 16 threads
 
 enum NccMode { N_STATS = 0, N_COST = 1, N_CONF = 2, N_SHIFT = 3, N_REFINE = 4, N_SWEEP = 5,
-               N_SWEEP_DUMP = 6 };          // the sweep that also writes the (D,N,H,W) NCC volume (tests only)
+               N_SWEEP_DUMP = 6,            // the sweep that also writes the (D,N,H,W) NCC volume (tests only)
+               N_VPROP = 7 };               // view propagation (extension): candidate depth + normal maps, adoption mask
 
 struct NccArgs {
     CUtensorMap tm_r;                        // reference gray, dims (W+PAD,H), pixel x at column x+PAD
@@ -50,6 +51,7 @@ struct NccArgs {
     int dy, dx;                              // N_SHIFT neighbour offset (candidate normal)
     int color;                               // N_SHIFT: -1 = every pixel may adopt the candidate (reference schedule);
                                              // 0 / 1 = only pixels with (x + y) & 1 == color (red-black extension)
+    const uint8_t *allow;                    // N_VPROP: 1 = this pixel's candidate is a real proposal (may be adopted)
     float nr;                                // N_REFINE normal range
     const float *rand_n;                     // injected N(0,1) (H,W,3) of this evaluation or NULL
     uint64_t seed;
@@ -189,6 +191,20 @@ __device__ __forceinline__ void box_sums(const float *__restrict__ s_s, const fl
     box_row<K, false, true>(s_s + base + K * RWP, s_r + base + K * RWP, as, ass, ars);
 }
 
+// Plane sweep: `ncc > thresh` for ncc = cov / sqrt(x), x = var1*var2 + 1e-8 (dense_stereo.py:303, 344-345), decided
+// without the square root and the division whenever cov^2 is clearly off thresh^2 * x (t_lo = (0.999 thresh)^2,
+// t_hi = (1.001 thresh)^2: margins four orders above the rounding errors involved); only the sliver around the
+// threshold, zero / negative / non-finite x, and a disabled quick test (t_lo == 0) take the exact path.
+__device__ __forceinline__ bool sweep_over(float cov, float x, float thresh, float t_lo, float t_hi) {
+    const float c2 = mul(cov, cov);
+    const bool cpos = cov > 0.0f, xpos = x > 0.0f;                                  // both false for NaN
+    const bool sure_f = !cpos | (xpos & (c2 < mul(x, t_lo)));                        // ncc <= 0, -inf, NaN, or clearly below
+    const bool sure_t = cpos & xpos & (c2 > mul(x, t_hi));                           // clearly above
+    bool over = sure_t;
+    if (!(sure_f | sure_t) | !(t_lo > 0.0f)) over = div_(cov, __fsqrt_rn(x)) > thresh;
+    return over;
+}
+
 template <int K, int MODE>
 __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_constant__ NccArgs a) {
     using G = Geo<K>;
@@ -323,13 +339,7 @@ __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_
                         if (gx < W && gy < H) a.ncc[(((size_t)a.plane * S + s) * H + gy) * W + gx] = ncc;
                         over = ncc > a.thresh;
                     } else {
-                        // branch-free decision; only the undecided sliver (or a disabled quick test) takes the exact path
-                        const float c2 = mul(cov, cov);
-                        const bool cpos = cov > 0.0f, xpos = x > 0.0f;                      // both false for NaN
-                        const bool sure_f = !cpos | (xpos & (c2 < mul(x, a.t_lo)));          // ncc <= 0, -inf, NaN, or clearly below
-                        const bool sure_t = cpos & xpos & (c2 > mul(x, a.t_hi));              // clearly above
-                        over = sure_t;
-                        if (!(sure_f | sure_t) | !(a.t_lo > 0.0f)) over = div_(cov, __fsqrt_rn(x)) > a.thresh;
+                        over = sweep_over(cov, x, a.thresh, a.t_lo, a.t_hi);
                     }
                     if (over && valid) total[q][p] = add(total[q][p], 1.0f);                  // :303-304
                 } else {
@@ -349,7 +359,7 @@ __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_
     // avg = total / (count + 1e-8) (:387) for the eight outputs, batched through the branch-free division like the NCC
     // above (the divisor is 1e-8, 1, 2, ..., S: always a trusted one)
     float avgv[QY][PX];
-    if (MODE == N_COST || MODE == N_SHIFT || MODE == N_REFINE) {
+    if (MODE == N_COST || MODE == N_SHIFT || MODE == N_REFINE || MODE == N_VPROP) {
         unsigned bad = 0;
 #pragma unroll
         for (int q = 0; q < QY; ++q)
@@ -404,6 +414,7 @@ __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_
             const float best = a.best_in[g];
             bool better = cost < best;                                                        // strict; NaN never wins
             if (MODE == N_SHIFT && a.color >= 0) better = better && ((gx + gy) & 1) == a.color;
+            if (MODE == N_VPROP) better = better && (__ldg(a.allow + g) != 0);
             if (better) a.depth_out[g] = __ldg(a.cand + g);
             else if (a.depth_out != a.depth_in) a.depth_out[g] = a.depth_in[g];
             if (better || a.best_out != a.best_in) a.best_out[g] = better ? cost : best;
@@ -412,6 +423,15 @@ __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_
                 // over when the evaluation is not in place
                 wins |= better ? 1u << (q * PX + p) : 0u;
                 if (!better && a.normal_out != a.normal_in) {
+                    const float *np = a.normal_in + 3 * g;
+                    float *no = a.normal_out + 3 * g;
+                    no[0] = np[0]; no[1] = np[1]; no[2] = np[2];
+                }
+                continue;
+            }
+            if (MODE == N_VPROP) {
+                // the candidate normal map (normal_in) is adopted by the winners; everybody else keeps the state
+                if (better) {
                     const float *np = a.normal_in + 3 * g;
                     float *no = a.normal_out + 3 * g;
                     no[0] = np[0]; no[1] = np[1]; no[2] = np[2];

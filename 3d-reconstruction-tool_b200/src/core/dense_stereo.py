@@ -3,8 +3,10 @@
 
 Same class / function names, constructor keywords, `reconstruct` signature, return types,
 stdout banners and empty-result conventions as the reference.  The (plane x neighbour) loop that
-the reference runs as ~45 eager PyTorch kernels per iteration is one kernel launch per reference
-view here (b200d_plane_sweep); masking + back-projection is b200d_mask_backproject.
+the reference runs as ~45 eager PyTorch kernels per (plane, neighbour) is two kernel launches per
+plane here, enqueued by one b200d_plane_sweep call per reference view: a sampling kernel over all
+neighbours and an NCC kernel that keeps the running (best count, first index) -- no (D,H,W) volume
+exists; masking + back-projection is b200d_mask_backproject.
 No CPU fallback: without a CUDA device the compute methods raise B200DenseError (the reference's
 `_plane_sweep_numpy` SSD fallback computes a different metric and is not reproduced).
 """
@@ -22,7 +24,8 @@ from .camera import Camera, CameraPose
 
 class DenseStereoReconstructor:
     def __init__(self, camera: Camera, scale: float = 0.25, num_depths: int = 64, patch_size: int = 5,
-                 min_views: int = 3, consistency_thresh: float = 0.8, *, num_neighbors: int = 6, device=None):
+                 min_views: int = 3, consistency_thresh: float = 0.8, *, num_neighbors: int = 6, device=None,
+                 arith: str = 'parity'):
         self.camera = camera
         self.scale = scale
         self.num_depths = num_depths
@@ -30,6 +33,9 @@ class DenseStereoReconstructor:
         self.min_views = min_views
         self.consistency_thresh = consistency_thresh
         self.num_neighbors = num_neighbors
+        if arith not in ('parity', 'fast'):
+            raise ValueError("arith must be 'parity' (bit-exact, default) or 'fast' (opt-in, not bit-exact)")
+        self.arith = arith
         self.device = torch.device(device) if device is not None else torch.device('cuda')
         self._engine = None
         self.views_in_flight = 2            # independent reference views enqueued concurrently (streams)
@@ -117,25 +123,39 @@ class DenseStereoReconstructor:
         rank, ws = bdist.world()
         eng = self.engine
         Kinv = np.linalg.inv(self.K_scaled)
-        jobs, job_views = [], []
+        plan = []
         for pos in range(rank, len(ref_indices), ws):
             ref_idx = ref_indices[pos]
             neighbors = self._find_neighbors(ref_idx, camera_indices, poses, k=self.num_neighbors)
-            if len(neighbors) < 2:
-                continue
-
+            if len(neighbors) >= 2:
+                plan.append((pos, ref_idx, neighbors))
+        # every image this rank reads is uploaded (and prepared) on the copy stream first; a job waits for the events of
+        # its own images, so no kernel on one stream can read an image another stream is still producing
+        ready = {}
+        copy_stream = eng.copy_stream()
+        copy_stream.wait_stream(torch.cuda.current_stream(eng.device))
+        with torch.cuda.stream(copy_stream):
+            for _, ref_idx, neighbors in plan:
+                for i in [ref_idx] + list(neighbors):
+                    if i not in ready:
+                        self._gray_on_device(processed, i)
+                        ready[i] = torch.cuda.Event()
+                        ready[i].record(copy_stream)
+        jobs = []
+        for pos, ref_idx, neighbors in plan:
             def job(slot, ref_idx=ref_idx, neighbors=neighbors):
+                st = torch.cuda.current_stream(eng.device)
+                for i in [ref_idx] + list(neighbors):
+                    st.wait_event(ready[i])
                 out = self._sweep_device(ref_idx, neighbors, processed, poses, depth_min, depth_max, slot=slot)
                 bgr = self._color_on_device(processed, ref_idx)
                 return eng.mask_backproject(out['depth_map'], out['confidence'], bgr, Kinv, poses[ref_idx].R,
                                             poses[ref_idx].t, float(self.min_views - 0.5), 1, sync=False, slot=slot)
             jobs.append(job)
-            job_views.append((pos, ref_idx))
         results = eng.run_views(jobs, self.views_in_flight)
-        torch.cuda.current_stream().synchronize()
+        counts = torch.cat([cnt for _, _, cnt in results]).cpu().tolist() if results else []   # one synchronisation
         local = {}
-        for (pos, ref_idx), (pts, cols, cnt) in zip(job_views, results):
-            m = int(cnt.item())
+        for (pos, ref_idx, _), (pts, cols, _), m in zip(plan, results, counts):
             local[ref_idx] = (pts[:m], cols[:m])
             print(f"  [{pos+1}/{len(ref_indices)}] Cam {ref_idx}: {m:,} pts")
         pts_d, col_d = bdist.gather_point_clouds(ref_indices, local, eng.device)
@@ -214,7 +234,8 @@ class DenseStereoReconstructor:
         depths = self._plane_depths(depth_min, depth_max).astype(np.float32)
         return eng.plane_sweep(self._gray_on_device(processed, ref_idx),
                                [self._gray_on_device(processed, i) for i in neighbor_indices], cams, depths,
-                               self.patch_size, self.consistency_thresh, slot=slot)
+                               self.patch_size, self.consistency_thresh, slot=slot,
+                               arith=1 if self.arith == 'fast' else 0)
 
     def _backproject(self, depth_map: np.ndarray, confidence: np.ndarray, color_map: np.ndarray,
                      pose: CameraPose, min_confidence: float) -> Tuple[np.ndarray, np.ndarray]:

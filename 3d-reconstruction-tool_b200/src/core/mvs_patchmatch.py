@@ -13,8 +13,12 @@ What differs, by design:
   * extra keyword-only constructor arguments: `num_src_views` (the reference hard-codes k=4 at
     :108), `rng` ('philox' = counter-based in-kernel generator; 'torch' = draw on the host with
     torch.rand/randn in the reference's call order, which makes results bit-identical to the
-    reference's CPU run under the same torch.manual_seed), `seed`, `device`, and two opt-in extensions the
-    reference has no counterpart for: `consistency='geometric'` and `schedule='redblack'` (checkerboard propagation).
+    reference's CPU run under the same torch.manual_seed), `seed`, `device`, `arith` ('parity' = bit-exact,
+    the default; 'fast' = the opt-in re-associated arithmetic, NOT bit-exact, see include/b200dense.h), and
+    three opt-in extensions the reference has no counterpart for: `consistency='geometric'` (cross-view
+    depth-map check), `schedule='redblack'` (checkerboard propagation) and `schedule='viewprop'` (after every
+    iteration the source views' current hypotheses are proposed to the reference view; the depth and normal
+    maps of all views are exchanged by an NCCL all-gather when the views are sharded over GPUs).
 """
 from __future__ import annotations
 
@@ -42,7 +46,7 @@ class PatchMatchMVS:
                  num_samples: int = 8, min_views: int = 3, depth_min: float = 0.1, depth_max: float = 100.0,
                  *, num_src_views: int = 4, rng: str = 'philox', seed: int = 0, device=None,
                  consistency: str = 'photometric', geo_min_views: int = 2, geo_px_thresh: float = 1.0,
-                 geo_rel_thresh: float = 0.01, schedule: str = 'reference'):
+                 geo_rel_thresh: float = 0.01, schedule: str = 'reference', arith: str = 'parity'):
         self.camera = camera
         self.scale = scale
         self.patch_size = patch_size
@@ -59,9 +63,13 @@ class PatchMatchMVS:
         if consistency not in ('photometric', 'geometric'):
             raise ValueError("consistency must be 'photometric' (the reference's check) or 'geometric' (extension)")
         self.consistency = consistency
-        if schedule not in ('reference', 'redblack'):
-            raise ValueError("schedule must be 'reference' (the reference's Jacobi shifts) or 'redblack' (extension)")
+        if schedule not in ('reference', 'redblack', 'viewprop'):
+            raise ValueError("schedule must be 'reference' (the reference's Jacobi shifts), 'redblack' or 'viewprop' "
+                             "(extensions)")
         self.schedule = schedule
+        if arith not in ('parity', 'fast'):
+            raise ValueError("arith must be 'parity' (bit-exact, default) or 'fast' (opt-in, not bit-exact)")
+        self.arith = arith
         self.geo_min_views, self.geo_px_thresh, self.geo_rel_thresh = geo_min_views, geo_px_thresh, geo_rel_thresh
         self.device = torch.device(device) if device is not None else torch.device('cuda')
         self.cache_images = True            # keep uploaded grays on the device between views
@@ -70,7 +78,8 @@ class PatchMatchMVS:
         self.device_prepare = True          # run _prepare_images on the GPU (bit-identical to the OpenCV calls)
         self._engine = None
         self._dev_gray: Dict[int, Tuple[int, torch.Tensor]] = {}
-        self._dev_maps: Dict[int, dict] = {}
+        self._kinv32 = None
+        self.last_timings: Dict[str, float] = {}   # phase breakdown of the last reconstruct() (seconds)
         if torch.cuda.is_available():
             print(f"PatchMatch MVS using GPU: {torch.cuda.get_device_name()}")
         else:
@@ -122,6 +131,34 @@ class PatchMatchMVS:
             self._dev_gray[idx] = (id(g), t)
         return t
 
+    def _stage_images(self, images: Dict, indices) -> Dict[int, "torch.cuda.Event"]:
+        """Upload (and, on the device-prepare path, resize + gray) the listed images on the copy stream, in order of
+        first use, and return one event per image.  A job on another stream waits for the events of the images it
+        reads before it launches anything, so no kernel can read an image whose upload / prepare kernel is still in
+        flight on a different stream; the first views start while later images are still crossing PCIe."""
+        eng = self.engine
+        ready: Dict[int, torch.cuda.Event] = {}
+        copy_stream = eng.copy_stream()
+        copy_stream.wait_stream(torch.cuda.current_stream(eng.device))
+        with torch.cuda.stream(copy_stream):
+            for i in indices:
+                if i in ready:
+                    continue
+                if 'gray' in images[i] and not self.cache_images:
+                    continue                             # uncached host grays are uploaded by the job, on its own stream
+                self._gray_on_device(images, i)
+                ready[i] = torch.cuda.Event()
+                ready[i].record(copy_stream)
+        return ready
+
+    @staticmethod
+    def _wait_images(ready: Dict, indices) -> None:
+        st = torch.cuda.current_stream()
+        for i in indices:
+            ev = ready.get(i)
+            if ev is not None:
+                st.wait_event(ev)
+
     # ------------------------------------------------------------------ public API
     def reconstruct(self, images: List[dict], poses: Dict[int, CameraPose],
                     sparse_points: np.ndarray = None) -> Tuple[np.ndarray, np.ndarray]:
@@ -130,7 +167,10 @@ class PatchMatchMVS:
         Views are independent, so they are (a) sharded round-robin over the ranks of an initialised
         torch.distributed job (one process per GPU; without one this is a single-GPU run) and (b) kept
         `views_in_flight` at a time on separate streams of each GPU.  Rank 0 returns the fused and filtered
-        cloud in the reference's order (sorted views, row-major pixels); other ranks return (0,3) arrays."""
+        cloud in the reference's order (sorted views, row-major pixels); other ranks return (0,3) arrays.
+        The fusion stage synchronises with the host once (to size the cloud): every view's mask is counted on the
+        device, then each view is back-projected straight into its slice of the final buffer -- on rank 0 the other
+        ranks' slices arrive by NCCL point-to-point transfers into place."""
         from b200dense import dist as bdist
         rank, ws = bdist.world()
         print("\n" + "=" * 60)
@@ -138,6 +178,7 @@ class PatchMatchMVS:
         print(f"  Scale: {self.scale}x, Patch: {self.patch_size}, Iters: {self.num_iterations}")
         print("=" * 60)
         t0 = time.time()
+        tm = self.last_timings = {}
         cam_indices = sorted(poses.keys())
         n_cams = len(cam_indices)
         if n_cams < 3:
@@ -152,68 +193,168 @@ class PatchMatchMVS:
 
         print(f"\nComputing depth maps for {n_cams} views...")
         self._dev_gray.clear()
-        self._dev_maps.clear()
         eng = self.engine
+        dev = eng.device
         Kinv = np.linalg.inv(self.K_scaled)
-        jobs, job_views = [], []
+        plan = []
         for pos in range(rank, n_cams, ws):
             ref_idx = cam_indices[pos]
             src_indices = self._select_source_views(ref_idx, cam_indices, poses, k=self.num_src_views)
             if len(src_indices) < 2:
                 print(f"  [{pos+1}/{n_cams}] Cam {ref_idx}: skipped (not enough neighbors)")
                 continue
-            jobs.append(lambda slot, r=ref_idx, s=src_indices: self._patchmatch_device(r, s, proc_images, poses, slot=slot))
-            job_views.append((pos, ref_idx, src_indices))
+            plan.append((pos, ref_idx, src_indices))
+        need = [i for _, r, src in plan for i in [r] + list(src)]
+        ready = self._stage_images(proc_images, need)
         # host-drawn random numbers must be consumed in view order -> one view at a time in that mode
-        results = eng.run_views(jobs, 1 if self.rng == 'torch' else self.views_in_flight)
-        maps = {ref_idx: out for (_, ref_idx, _), out in zip(job_views, results)}
-
+        in_flight = 1 if self.rng == 'torch' else self.views_in_flight
+        if self.schedule == 'viewprop':
+            maps = self._run_viewprop(plan, cam_indices, proc_images, poses, ready, in_flight)
+        else:
+            def view_job(ref_idx, src_indices):
+                def job(slot):
+                    self._wait_images(ready, [ref_idx] + list(src_indices))
+                    return self._patchmatch_device(ref_idx, src_indices, proc_images, poses, slot=slot)
+                return job
+            results = eng.run_views([view_job(r, s) for _, r, s in plan], in_flight)
+            maps = {ref_idx: out for (_, ref_idx, _), out in zip(plan, results)}
         if self.consistency == 'geometric':
-            # EXTENSION (no reference counterpart): cross-view geometric check.  The depth maps of the other ranks'
-            # views arrive by one NCCL all-gather; the check itself is again view-local.
-            H, W = next(iter(proc_images.values()))['shape']
-            all_depth = bdist.all_gather_maps(cam_indices, {v: o['depth'] for v, o in maps.items()}, (H, W), eng.device)
-            computed = bdist.all_gather_maps(cam_indices, {v: torch.ones(1, device=eng.device) for v in maps}, (1,),
-                                             eng.device)
-            for _, ref_idx, src_indices in job_views:
-                srcs = [i for i in src_indices if float(computed[i].item()) > 0]
-                if not srcs:
-                    maps[ref_idx]['confidence'].zero_()
-                    continue
-                from b200dense.engine import kinv32, make_cams
-                cams = make_cams(self.K_scaled, kinv32(self.K_scaled), poses[ref_idx].R, poses[ref_idx].t,
-                                 [poses[i].R for i in srcs], [poses[i].t for i in srcs])
-                geo = eng.geo_consistency(maps[ref_idx]['depth'], [all_depth[i].contiguous() for i in srcs], cams,
-                                          self.geo_px_thresh, self.geo_rel_thresh)
-                conf = maps[ref_idx]['confidence']
-                maps[ref_idx]['confidence'] = torch.where(geo >= float(self.geo_min_views), conf, torch.zeros_like(conf))
+            self._geometric_filter(plan, cam_indices, proc_images, poses, maps)
 
-        local = {}
-        for pos, ref_idx, _ in job_views:
+        # ---- fusion: count every mask on the device, read the counts once, back-project into place
+        counts_d = torch.zeros(max(1, len(plan)), dtype=torch.int64, device=dev)
+        for j, (_, ref_idx, _) in enumerate(plan):
             out = maps[ref_idx]
-            bgr = self._color_on_device(proc_images, ref_idx)
-            pts, cols = eng.mask_backproject(out['depth'], out['confidence'], bgr, Kinv, poses[ref_idx].R,
-                                             poses[ref_idx].t, float(self.min_views), 0)
-            local[ref_idx] = (pts.clone(), cols.clone())
-            print(f"  [{pos+1}/{n_cams}] Cam {ref_idx}: {pts.shape[0]:,} valid pixels")
+            eng.mask_count(out['depth'], out['confidence'], float(self.min_views), 0, counts_d[j:j + 1])
+        counts_h = counts_d.cpu().tolist()                      # the one host synchronisation of the depth + fusion stage
+        tm['depth_maps_s'] = time.time() - t0
+        local_counts = {pos: int(c) for (pos, _, _), c in zip(plan, counts_h)}
+        for (pos, ref_idx, _), c in zip(plan, counts_h):
+            print(f"  [{pos+1}/{n_cams}] Cam {ref_idx}: {int(c):,} valid pixels")
 
         print("\nFusing depth maps...")
-        pts_d, col_d = bdist.gather_point_clouds(cam_indices, local, eng.device)
+        t1 = time.time()
+        all_counts = bdist.exchange_counts(n_cams, local_counts, dev)
+        offs = np.concatenate([[0], np.cumsum(all_counts)]).astype(np.int64)
+        total = int(offs[-1])
+        if rank == 0:
+            buf_p = torch.empty((total, 3), dtype=torch.float64, device=dev)
+            buf_c = torch.empty((total, 3), dtype=torch.uint8, device=dev)
+            base = {pos: int(offs[pos]) for pos, _, _ in plan}
+        else:
+            mine = int(sum(local_counts.values()))
+            buf_p = torch.empty((mine, 3), dtype=torch.float64, device=dev)
+            buf_c = torch.empty((mine, 3), dtype=torch.uint8, device=dev)
+            run, base = 0, {}
+            for pos, _, _ in plan:
+                base[pos] = run
+                run += local_counts[pos]
+        local = {}
+        dummy = torch.zeros(1, dtype=torch.int64, device=dev)
+        for pos, ref_idx, _ in plan:
+            m, b = local_counts[pos], base[pos]
+            if m == 0:
+                continue
+            out = maps[ref_idx]
+            sl = (buf_p[b:b + m], buf_c[b:b + m])
+            eng.mask_backproject(out['depth'], out['confidence'], self._color_on_device(proc_images, ref_idx), Kinv,
+                                 poses[ref_idx].R, poses[ref_idx].t, float(self.min_views), 0, points=sl[0],
+                                 colors=sl[1], count=dummy, sync=False)
+            local[pos] = sl
+        bdist.gather_into(all_counts, local, buf_p if rank == 0 else None, buf_c if rank == 0 else None)
+        tm['fusion_gather_s'] = time.time() - t1
         if rank != 0:
+            torch.cuda.current_stream(dev).synchronize()
             return np.array([]).reshape(0, 3), np.array([]).reshape(0, 3)
+        pts_d, col_d = buf_p, buf_c
         print(f"  Raw points: {pts_d.shape[0]:,}")
+        t2 = time.time()
         if pts_d.shape[0] == 0:
             points, colors = np.array([]).reshape(0, 3), np.array([]).reshape(0, 3)
         elif self.device_postfilter:
             from b200dense.postfilter import filter_points
             fp, fc = filter_points(pts_d, col_d)                 # same selection and order as _filter_points
-            points, colors = fp.cpu().numpy(), fc.cpu().numpy()
+            points, colors = eng.to_host([fp, fc])
             print(f"  After filtering: {len(points):,}")
         else:
             points, colors = self._filter_points(pts_d.cpu().numpy(), col_d.cpu().numpy())
             print(f"  After filtering: {len(points):,}")
+        tm['filter_download_s'] = time.time() - t2
+        tm['raw_points'] = int(pts_d.shape[0])
+        tm['total_s'] = time.time() - t0
         print(f"\nPatchMatch MVS completed in {time.time() - t0:.1f}s")
         return points, colors
+
+    def _geometric_filter(self, plan, cam_indices, proc_images, poses, maps) -> None:
+        """EXTENSION (no reference counterpart): cross-view geometric check.  The depth maps of the other ranks' views
+        arrive by one NCCL all-gather; the check itself is again view-local.  Confidence is zeroed where fewer than
+        `geo_min_views` sources agree geometrically."""
+        from b200dense import dist as bdist
+        eng = self.engine
+        H, W = next(iter(proc_images.values()))['shape']
+        all_depth = bdist.all_gather_maps(cam_indices, {v: o['depth'] for v, o in maps.items()}, (H, W), eng.device)
+        computed = bdist.all_gather_maps(cam_indices, {v: torch.ones(1, device=eng.device) for v in maps}, (1,),
+                                         eng.device)
+        has_map = {v: float(t.item()) > 0 for v, t in computed.items()}
+        for _, ref_idx, src_indices in plan:
+            srcs = [i for i in src_indices if has_map[i]]
+            if not srcs:
+                maps[ref_idx]['confidence'].zero_()
+                continue
+            cams = self._camera_block(ref_idx, srcs, poses)
+            geo = eng.geo_consistency(maps[ref_idx]['depth'], [all_depth[i].contiguous() for i in srcs], cams,
+                                      self.geo_px_thresh, self.geo_rel_thresh)
+            conf = maps[ref_idx]['confidence']
+            maps[ref_idx]['confidence'] = torch.where(geo >= float(self.geo_min_views), conf, torch.zeros_like(conf))
+
+    def _run_viewprop(self, plan, cam_indices, images, poses, ready, in_flight) -> Dict[int, dict]:
+        """EXTENSION `schedule='viewprop'` (the reference's README names view propagation, its code has none): all
+        views advance in lock step.  After every PatchMatch iteration the depth AND normal maps of all views are
+        exchanged (NCCL all-gather when views are sharded; the snapshot makes the result independent of the number of
+        GPUs) and each view evaluates, per source view, the hypothesis that source currently holds for the same
+        surface point (b200d_pm_viewprop); then the next iteration.  The confidence pass runs at the end."""
+        from b200dense import _cabi, dist as bdist
+        eng = self.engine
+        dev = eng.device
+        st, rngs = {}, {}
+        arith = self._arith_code()
+        for _, r, _ in plan:
+            H, W = images[r]['shape']
+            st[r] = dict(depth=torch.empty((H, W), device=dev), normal=torch.empty((H, W, 3), device=dev),
+                         confidence=torch.empty((H, W), device=dev), best_cost=torch.empty((H, W), device=dev))
+            rngs[r] = ({k: v.to(dev, non_blocking=True).contiguous() for k, v in self._host_rng(H, W).items()}
+                       if self.rng == 'torch' else {})
+        H, W = next(iter(images.values()))['shape']
+        iters = self.num_iterations
+
+        def pm_stage(r, src, it_begin, it_end, stage):
+            def job(slot):
+                self._wait_images(ready, [r] + list(src))
+                return eng.pm_view(self._gray_on_device(images, r), [self._gray_on_device(images, i) for i in src],
+                                   self._camera_block(r, src, poses), self.patch_size, iters, self.num_samples,
+                                   self.depth_min, self.depth_max, seed=self.seed, view_id=int(r), slot=slot, out=st[r],
+                                   arith=arith, it_begin=it_begin, it_end=it_end, stage=stage, **rngs[r])
+            return job
+
+        if iters == 0:
+            eng.run_views([pm_stage(r, src, 0, 0, 0) for _, r, src in plan], in_flight)
+            return st
+        for it in range(iters):
+            stage = _cabi.STAGE_NO_CONF | (_cabi.STAGE_NO_INIT if it > 0 else 0)
+            eng.run_views([pm_stage(r, src, it, it + 1, stage) for _, r, src in plan], in_flight)
+            all_depth = bdist.all_gather_maps(cam_indices, {r: st[r]['depth'] for r in st}, (H, W), dev)
+            all_normal = bdist.all_gather_maps(cam_indices, {r: st[r]['normal'] for r in st}, (H, W, 3), dev)
+
+            def vp_job(r, src):
+                def job(slot):
+                    eng.pm_viewprop(self._gray_on_device(images, r), [self._gray_on_device(images, i) for i in src],
+                                    self._camera_block(r, src, poses), self.patch_size, self.depth_min, self.depth_max,
+                                    [all_depth[i] for i in src], [all_normal[i] for i in src], st[r], arith=arith,
+                                    slot=slot)
+                return job
+            eng.run_views([vp_job(r, src) for _, r, src in plan], in_flight)
+        eng.run_views([pm_stage(r, src, iters, 0, _cabi.STAGE_NO_INIT) for _, r, src in plan], in_flight)
+        return st
 
     # ------------------------------------------------------------------ host heuristics
     def _estimate_depth_range(self, poses: Dict[int, CameraPose], sparse_points: np.ndarray = None):
@@ -265,9 +406,15 @@ class PatchMatchMVS:
         return [idx for idx, _ in scored[:k]]
 
     # ------------------------------------------------------------------ device path
+    def _arith_code(self) -> int:
+        return 1 if self.arith == 'fast' else 0
+
     def _camera_block(self, ref_idx, src_indices, poses):
         from b200dense.engine import kinv32, make_cams
-        return make_cams(self.K_scaled, kinv32(self.K_scaled), poses[ref_idx].R, poses[ref_idx].t,
+        key = self.K_scaled.tobytes()
+        if self._kinv32 is None or self._kinv32[0] != key:      # one fp32 inverse per intrinsics, not per view
+            self._kinv32 = (key, kinv32(self.K_scaled))
+        return make_cams(self.K_scaled, self._kinv32[1], poses[ref_idx].R, poses[ref_idx].t,
                          [poses[i].R for i in src_indices], [poses[i].t for i in src_indices])
 
     def _host_rng(self, H: int, W: int) -> dict:
@@ -301,7 +448,7 @@ class PatchMatchMVS:
             kw = {k: v.to(eng.device, non_blocking=True).contiguous() for k, v in self._host_rng(H, W).items()}
         return eng.pm_view(ref, srcs, self._camera_block(ref_idx, src_indices, poses), self.patch_size,
                            self.num_iterations, self.num_samples, self.depth_min, self.depth_max,
-                           seed=self.seed, view_id=int(ref_idx), slot=slot,
+                           seed=self.seed, view_id=int(ref_idx), slot=slot, arith=self._arith_code(),
                            schedule=1 if self.schedule == 'redblack' else 0, **kw)
 
     def compute_depth_maps(self, images: Dict, poses: Dict[int, CameraPose], ref_indices: List[int] = None,
@@ -313,6 +460,8 @@ class PatchMatchMVS:
         through pinned staging on its own stream, so copies overlap the other views' kernels.  This is what
         `reconstruct()` does internally; views with fewer than two sources are skipped like there (:110-112)."""
         from b200dense.engine import PINNED
+        if self.schedule == 'viewprop':
+            raise ValueError("schedule='viewprop' couples the views: use reconstruct()")
         eng = self.engine
         all_indices = sorted(poses.keys())
         ref_indices = list(all_indices if ref_indices is None else ref_indices)
@@ -327,24 +476,11 @@ class PatchMatchMVS:
         if not keep:
             self._dev_gray.clear()                       # re-upload: the caller asked for no caching across calls
         try:
-            # uploads go to a copy stream in order of first use; a view waits only for its own images, so the first
-            # views start while the later views' images are still crossing PCIe
-            ready = {}
-            copy_stream = eng.copy_stream()
-            copy_stream.wait_stream(torch.cuda.current_stream(eng.device))
-            with torch.cuda.stream(copy_stream):
-                for r, src in plan:
-                    for i in [r] + src:
-                        if i not in ready:
-                            self._gray_on_device(images, i)
-                            ready[i] = torch.cuda.Event()
-                            ready[i].record(copy_stream)
+            ready = self._stage_images(images, [i for r, src in plan for i in [r] + src])
             jobs = []
             for r, src in plan:
                 def job(slot, r=r, src=src):
-                    st = torch.cuda.current_stream(eng.device)
-                    for i in [r] + src:
-                        st.wait_event(ready[i])
+                    self._wait_images(ready, [r] + src)
                     out = self._patchmatch_device(r, src, images, poses, slot=slot)
                     host = []
                     for k in ('depth', 'normal', 'confidence'):
@@ -363,7 +499,6 @@ class PatchMatchMVS:
         for (r, _), (out, host) in zip(plan, results):
             dm = DepthNormalMap(depth=PINNED.as_numpy(host[0]), normal=PINNED.as_numpy(host[1]),
                                 confidence=PINNED.as_numpy(host[2]))
-            self._dev_maps[r] = dict(owner=id(dm.depth), depth=out['depth'], confidence=out['confidence'])
             maps[r] = dm
         return maps
 
@@ -373,7 +508,6 @@ class PatchMatchMVS:
         out = self._patchmatch_device(ref_idx, src_indices, images, poses)
         depth, normal, conf = self.engine.to_host([out['depth'], out['normal'], out['confidence']])
         dm = DepthNormalMap(depth=depth, normal=normal, confidence=conf)
-        self._dev_maps[ref_idx] = dict(owner=id(dm.depth), depth=out['depth'], confidence=out['confidence'])
         return dm
 
     def _fuse_depth_maps(self, depth_maps: Dict[int, DepthNormalMap], images: Dict,
@@ -383,11 +517,9 @@ class PatchMatchMVS:
         Kinv = np.linalg.inv(self.K_scaled)
         all_points, all_colors = [], []
         for idx, dm in depth_maps.items():
-            dev = self._dev_maps.get(idx)
-            if dev is not None and dev['owner'] == id(dm.depth):
-                depth, conf = dev['depth'], dev['confidence']
-            else:
-                depth, conf = eng.to_device(dm.depth), eng.to_device(dm.confidence)
+            # always from the caller's host arrays, like the reference: edits made to a map after it was
+            # returned (own filtering, a replaced confidence) are honoured; the two maps are a few MB
+            depth, conf = eng.to_device(dm.depth), eng.to_device(dm.confidence)
             bgr = eng.to_device(images[idx]['color'], torch.uint8)
             pts, cols = eng.mask_backproject(depth, conf, bgr, Kinv, poses[idx].R, poses[idx].t,
                                              float(self.min_views), 0)

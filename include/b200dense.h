@@ -21,9 +21,15 @@
  * Arithmetic modes
  *   B200D_PARITY  IEEE-RN fp32 in the exact operation order of the reference's CPU path
  *                 (SURVEY.md §7.4): bit-identical to oracle/dense_oracle.c.
- *   B200D_FAST    reserved.  A re-associated variant (composed reprojection, separable window sums) was built
- *                 and measured: 1.6x faster but its NCC misses the 1e-4 tolerance wherever a patch is flat
- *                 (DESIGN.md 5.8), so it is not shipped; passing it returns B200D_ERR_UNSUPPORTED.
+ *                 In the plane sweep, which uses the NCC only through `ncc > thresh`, the comparison is decided
+ *                 from separable window sums plus a rigorous error bound and only undecided outputs redo the
+ *                 reference's chains: same counts / arg-max bit for bit (csrc/fast_kernels.cuh).
+ *   B200D_PARITY_CHAINS  same results as B200D_PARITY; the plane sweep evaluates the reference's chains for
+ *                 every output (the A/B twin of the bounded decision, used by tests and profiling).
+ *   B200D_FAST    OPT-IN, NOT BIT-EXACT, never the default: composed reprojection, direct bilinear lookup,
+ *                 separable window sums, MUFU reciprocal / rsqrt.  It misses the north_star tolerances wherever a
+ *                 patch is flat (var = E[x^2] - E[x]^2 is ill-conditioned) and its agreement with
+ *                 the oracle is measured and reported, never asserted as parity (tests/test_gpu_fast.py).
  */
 #ifndef B200DENSE_H
 #define B200DENSE_H
@@ -42,7 +48,7 @@ extern "C" {
 #endif
 
 #define B200D_MAX_SRC 8          /* source / neighbour views per reference view */
-#define B200D_ABI_VERSION 2
+#define B200D_ABI_VERSION 3
 
 typedef enum {
     B200D_OK = 0,
@@ -51,7 +57,7 @@ typedef enum {
     B200D_ERR_UNSUPPORTED = -3
 } b200d_status;
 
-typedef enum { B200D_PARITY = 0, B200D_FAST = 1 } b200d_arith;
+typedef enum { B200D_PARITY = 0, B200D_FAST = 1, B200D_PARITY_CHAINS = 2 } b200d_arith;
 
 /* Camera block, fp32, exactly what the reference uploads per reference view
  * (mvs_patchmatch.py:237-257, dense_stereo.py:232-259): K = K_scaled cast to fp32,
@@ -94,15 +100,21 @@ typedef struct {
      * the four axis neighbours are evaluated and only pixels of that colour may adopt them (8 evaluations), so the
      * second colour already sees the first colour's updates; refinement is unchanged. */
     int32_t schedule;
-    int32_t reserved;
+    /* Staged execution, for schedules that interleave the views between iterations (view propagation, an EXTENSION):
+     * run iterations [it_begin, it_end) only (it_end == 0 means `iters`), optionally without the initialisation
+     * (B200D_STAGE_NO_INIT: d_depth / d_normal / d_best already hold the state) and without the final confidence
+     * pass (B200D_STAGE_NO_CONF).  All zero = the whole view, which is the reference's `_patchmatch_cuda`. */
+    int32_t stage;
+    int32_t it_begin, it_end;
 } b200d_pm_params;
 
 typedef enum { B200D_SCHEDULE_REFERENCE = 0, B200D_SCHEDULE_REDBLACK = 1 } b200d_schedule;
+typedef enum { B200D_STAGE_NO_INIT = 1, B200D_STAGE_NO_CONF = 2 } b200d_stage;
 
 /* Device scratch of one view in flight, shared by all compute entry points below:
  * reference window statistics, candidate depth, validity bits, a pitch-padded copy of the reference
  * (TMA source when W is not a multiple of 4) and B200D_MAX_SRC pitch-padded sampled images
- * (~81 bytes per pixel).  Calls that may run concurrently (different streams) need different scratch. */
+ * (~65 bytes per pixel).  Calls that may run concurrently (different streams) need different scratch. */
 B200D_API size_t b200d_scratch_bytes(int H, int W);
 
 B200D_API int b200d_abi_version(void);
@@ -133,6 +145,20 @@ B200D_API int b200d_pm_view(const float *d_ref, const float *const *d_src, const
                   void *d_scratch, float *d_depth, float *d_normal, float *d_conf, float *d_best,
                   float *d_costs, void *stream);
 
+/* EXTENSION (the reference's README lists "view propagation", README.md:117, but its code has none -- SURVEY F2; no
+ * dackey-wav oracle): one propagation step from the source views' current hypotheses.  For every source s in turn:
+ * each reference pixel p at its current depth d is projected into s, the nearest pixel's depth d_s of s's depth map is
+ * back-projected and brought into the reference camera; its depth there (if inside [depth_min, depth_max]) with the
+ * normal R_ref R_s^T n_s is p's candidate, costed like any other hypothesis map and adopted where `cost < best`
+ * (pixels whose round trip fails keep their hypothesis and may not adopt).  d_src_depth[s] (H,W) and d_src_normal[s]
+ * (H,W,3) are SNAPSHOTS of the sources' maps (all-gathered over NCCL when the views are sharded); d_depth, d_normal,
+ * d_best are updated in place; d_costs (S,H,W) optional dump.  Definition restated in oracle/dense_oracle.c
+ * (orc_viewprop_candidates) + tests/test_gpu_viewprop.py; kernels csrc/geo_kernels.cuh. */
+B200D_API int b200d_pm_viewprop(const float *d_ref, const float *const *d_src, const b200d_cams *cams, int H, int W,
+                                const b200d_pm_params *prm, const float *const *d_src_depth,
+                                const float *const *d_src_normal, void *d_scratch, float *d_depth, float *d_normal,
+                                float *d_best, float *d_costs, void *stream);
+
 /* Replaces DenseStereoReconstructor._plane_sweep_torch (dense_stereo.py:222-316):
  * for each plane d (given order) and neighbour n: reproject at constant depth, bilinear sample,
  * box NCC (_compute_ncc_torch :318-347), count (ncc > thresh) & (z > 0.1); first arg-max over d.
@@ -143,6 +169,10 @@ B200D_API int b200d_plane_sweep(const float *d_ref, const float *const *d_nbr, c
                                 const float *depths, int D, int H, int W, int patch, float thresh, int arith,
                                 float *d_depth_map, float *d_conf, int32_t *d_idx, float *d_ncc, void *d_scratch,
                                 void *stream);
+
+/* Diagnostic (synchronises the device): number of (warp, neighbour) evaluations of the B200D_PARITY plane sweep whose
+ * bounded decision was inconclusive and which were redone with the reference's chains, since the last reset. */
+B200D_API int b200d_sweep_fallbacks(uint64_t *count, int reset);
 
 /* Replaces the per-view body of PatchMatchMVS._fuse_depth_maps (mvs_patchmatch.py:545-565, mode 0:
  * valid = conf >= min_conf) and DenseStereoReconstructor._backproject (dense_stereo.py:414-437,
@@ -155,6 +185,12 @@ B200D_API int b200d_mask_backproject(const float *d_depth, const float *d_conf, 
                            const double *Kinv64, const double *R64, const double *t64,
                            float min_conf, int mode, double *d_points, uint8_t *d_colors,
                            int64_t *d_count, void *d_scratch, void *stream);
+
+/* Count-only pass of the same mask (no points written): d_count (1 x int64) receives the number of valid pixels, so a
+ * caller can size one exact output buffer for many views with a single host synchronisation and then let
+ * b200d_mask_backproject write every view into its slice. */
+B200D_API int b200d_mask_count(const float *d_depth, const float *d_conf, int H, int W, float min_conf, int mode,
+                               int64_t *d_count, void *d_scratch, void *stream);
 
 /* Replaces `_prepare_images` (mvs_patchmatch.py:167-191, dense_stereo.py:156-176) for one image:
  * cv.resize(INTER_LINEAR) of the BGR uint8 image to (nh,nw), BGR2GRAY, /255 -- OpenCV's fixed-point arithmetic,
@@ -171,7 +207,8 @@ B200D_API int b200d_prepare_image(const uint8_t *d_bgr, int H, int W, int nh, in
 B200D_API int b200d_knn_mean_dist(const double *d_points, int64_t n, int k, double *d_mean_dist, void *stream);
 
 /* HOST function (no CUDA): replaces the per-point Python loop of save_ply (src/core/utils.py:8-37).  Writes the
- * same bytes: ASCII PLY header, then "%.6f %.6f %.6f %d %d %d" per vertex.  points (n,3) f64, colors (n,3) u8 RGB. */
+ * same bytes: ASCII PLY header, then "%.6f %.6f %.6f %d %d %d" per vertex.  points (n,3) f64, colors (n,3) u8 RGB.
+ * Vertices are formatted in parallel on the host threads (OpenMP) and written in order. */
 B200D_API int b200d_write_ply_ascii(const char *path, const double *points, const uint8_t *colors, int64_t n);
 
 /* EXTENSION (no counterpart in the reference, whose consistency check is photometric -- SURVEY F6): cross-view
@@ -191,11 +228,18 @@ B200D_API int b200d_geo_consistency(const float *d_depth_ref, const float *const
  * the intrinsics. */
 B200D_API int b200d_selftest_fast_math(uint64_t n_div, uint64_t *out8, void *stream);
 
+/* Diagnostic (synchronises): the FP32 roofline denominator measured on the current device -- sustained packed-FMA
+ * (FFMA2) rate in T lane-FMA/s (x2 = TFLOP/s), from a loop of independent fma.rn.f32x2 chains that exercises nothing
+ * but the FMA pipe (csrc/diag_kernels.cuh; nominal 148 SMs x 128 lanes x clock). */
+B200D_API int b200d_measure_fp32_peak(double *tlaneops, void *stream);
+
 /* Optional per-launch timing for benchmarks.  Between _begin and _end every tile kernel launched by
  * this library is bracketed by CUDA events on its own stream (library-owned events, at most
  * max_records launches).  _end waits for the recorded launches, writes their durations (ms) and tags
  * (NCC kernels: mode*100 + patch with mode 0 stats, 1 cost, 2 confidence, 3 shift, 4 refine, 5 plane
- * sweep, 6 plane sweep with the NCC dump; sampling kernels: 2000 + 10*candidate + bounds; init 3000; fusion 4000) and releases the events.  Not meant to be left on in production. */
+ * sweep, 6 plane sweep with the NCC dump, 7 view propagation; +10000 for the B200D_FAST twins, +20000 for the bounded
+ * plane sweep; sampling kernels: 2000 + 10*candidate + bounds (12000 + ... in B200D_FAST); init 3000; fusion 4000;
+ * geometric consistency 5000; view-propagation proposals 5100) and releases the events.  Not meant to be left on in production. */
 B200D_API int b200d_profile_begin(int max_records);
 B200D_API int b200d_profile_end(float *ms_out, int32_t *tag_out, int cap, int *n_out);
 

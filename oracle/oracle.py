@@ -157,3 +157,27 @@ def mask_backproject(depth, conf, bgr, Kinv64, R, t, min_conf, mode):
                                    Ki.ctypes.data_as(d), R.ctypes.data_as(d), t.ctypes.data_as(d),
                                    C.c_float(min_conf), int(mode), pts.ctypes.data_as(d), col.ctypes.data_as(u8))
     return pts, col
+
+
+def geo_consistency(depth_ref, depth_srcs, cams: Cams, px_thresh, rel_thresh):
+    """EXTENSION definition (no dackey-wav counterpart): number of sources whose depth map agrees with depth_ref."""
+    depth_ref = _f32(depth_ref)
+    ds = _f32(np.stack(depth_srcs))
+    H, W = depth_ref.shape
+    out = np.empty((H, W), _f)
+    lib().orc_geo_consistency(_p(depth_ref), _p(ds), ds.shape[0], H, W, *cams.args(), C.c_float(px_thresh),
+                              C.c_float(rel_thresh), _p(out))
+    return out
+
+
+def viewprop_candidates(depth, normal, depth_src, normal_src, s, cams: Cams, depth_min, depth_max):
+    """EXTENSION definition: view-propagation proposal (cand_depth, cand_normal, allow) from source `s` of `cams`."""
+    depth, normal = _f32(depth), _f32(normal)
+    depth_src, normal_src = _f32(depth_src), _f32(normal_src)
+    H, W = depth.shape
+    cd = np.empty((H, W), _f)
+    cn = np.empty((H, W, 3), _f)
+    al = np.empty((H, W), np.uint8)
+    lib().orc_viewprop_candidates(_p(depth), _p(normal), _p(depth_src), _p(normal_src), int(s), H, W, *cams.args(),
+                                  C.c_float(_f(depth_min)), C.c_float(_f(depth_max)), _p(cd), _p(cn), _p(al, C.c_uint8))
+    return cd, cn, al.astype(bool)

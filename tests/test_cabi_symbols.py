@@ -33,10 +33,10 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_abi_version_and_struct_layout():
     lib = _cabi.load()
-    assert lib.b200d_abi_version() == 2
+    assert lib.b200d_abi_version() == _cabi.ABI_VERSION == 3
     # b200d_cams: 9+9+9+3 floats, int32, 8*9 + 8*3 floats
     assert C.sizeof(_cabi.Cams) == 4 * (30 + 1 + 72 + 24)
-    assert C.sizeof(_cabi.PmParams) == 4 * 4 + 2 * 8 + 2 * 4
+    assert C.sizeof(_cabi.PmParams) == 4 * 4 + 2 * 8 + 4 * 4
     assert lib.b200d_scratch_bytes(1200, 1600) >= 16 * 1200 * 1600 * 4
     assert lib.b200d_scratch_bytes(0, 10) == 0
     assert lib.b200d_fuse_scratch_bytes(10, 10) > 0

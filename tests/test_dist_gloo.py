@@ -38,6 +38,26 @@ def _worker(rank, ws, port, q):
         pts, col = bdist.gather_point_clouds(VIEWS, local, torch.device('cpu'))
         maps = bdist.all_gather_maps(VIEWS, {v: torch.full((3, 4), float(v)) for v in mine}, (3, 4), torch.device('cpu'))
         ok_maps = all(torch.equal(maps[v], torch.full((3, 4), float(v))) for v in VIEWS)
+        # the copy-free gather reconstruct() uses: counts exchanged once, rank 0 receives straight into final slices
+        my_pos = list(range(rank, len(VIEWS), ws))
+        counts = bdist.exchange_counts(len(VIEWS), {p: COUNTS[VIEWS[p]] for p in my_pos}, torch.device('cpu'))
+        assert counts == [COUNTS[v] for v in VIEWS]
+        offs = np.concatenate([[0], np.cumsum(counts)])
+        total = int(offs[-1])
+        if rank == 0:
+            out_p = torch.full((total, 3), -7.0, dtype=torch.float64)
+            out_c = torch.zeros((total, 3), dtype=torch.uint8)
+            loc = {}
+            for p in my_pos:                                     # own views are written in place
+                cp, cc = _fake_cloud(VIEWS[p], COUNTS[VIEWS[p]])
+                out_p[offs[p]:offs[p + 1]] = cp
+                out_c[offs[p]:offs[p + 1]] = cc
+                loc[p] = (out_p[offs[p]:offs[p + 1]], out_c[offs[p]:offs[p + 1]])
+            bdist.gather_into(counts, loc, out_p, out_c)
+            ok_maps = ok_maps and torch.equal(out_p, pts) and torch.equal(out_c, col)
+        else:
+            loc = {p: _fake_cloud(VIEWS[p], COUNTS[VIEWS[p]]) for p in my_pos}
+            bdist.gather_into(counts, loc, None, None)
         q.put((rank, pts.numpy(), col.numpy(), ok_maps))
     finally:
         dist.destroy_process_group()

@@ -165,3 +165,31 @@ def test_config4_shape_patchmatch_3840x2160(engine):
     epts, ecol = orc.mask_backproject(o['depth'], o['confidence'], bgr, Kinv64, sc.poses[ref][0], sc.poses[ref][1], 2.0, 0)
     assert pts.shape[0] == epts.shape[0] and np.array_equal(col.cpu().numpy(), ecol)
     np.testing.assert_allclose(pts.cpu().numpy(), epts, rtol=0, atol=1e-9)
+
+
+@pytest.mark.timeout(900)
+def test_config3_benchmark_shape_1600x1200_injected_rng_vs_oracle(engine):
+    """The benchmark's own shape (1600x1200, S=5, k=11; 1200 / 32 = 37.5 tile rows: a ragged bottom row of tiles) with
+    injected RNG against the oracle, bit for bit: 1 iteration, 1 sample (2 shifts + 1 refinement + confidence) on the
+    benchmark's turntable scene and source selection."""
+    W, H, k, S = 1600, 1200, 11, 5
+    sc = make_scene('turntable', 64, W, H, arc_deg=360.0 / 64, seed=0, device='cuda', render=list(range(0, 12)))
+    gray = gray_f32(sc)
+    ref, src = 5, [3, 7, 2, 8, 1][:S]
+    ecams, ocams = _cams(sc, ref, src)
+    dmin, dmax = sc.depth_range
+    g = np.random.default_rng(31)
+    depth0 = np.exp(g.random((H, W), dtype=np.float32) * np.float32(np.log(dmax) - np.log(dmin)) + np.float32(np.log(dmin)))
+    n0 = g.standard_normal((H, W, 3), dtype=np.float32) * np.float32(0.3)
+    n0[..., 2] = -1
+    n0 /= np.linalg.norm(n0, axis=-1, keepdims=True)
+    ru = g.random((1, H, W), dtype=np.float32)
+    rn = g.standard_normal((1, H, W, 3), dtype=np.float32)
+    d = engine.to_device
+    out = engine.pm_view(d(gray[ref]), [d(gray[i]) for i in src], ecams, k, 1, 1, dmin, dmax, init_depth=d(depth0),
+                         init_normal=d(n0), rand_u=d(ru), rand_n=d(rn), want_best=True, dump_costs=True)
+    exp = orc.pm_view(gray[ref], [gray[i] for i in src], ocams, k, 1, 1, dmin, dmax, depth0, n0, ru, rn, dump_costs=True)
+    assert np.array_equal(out['costs'].cpu().numpy(), exp['costs'], equal_nan=True)
+    for key in ('depth', 'normal', 'confidence', 'best_cost'):
+        assert np.array_equal(out[key].cpu().numpy(), exp[key], equal_nan=True), key
+    assert np.isfinite(exp['best_cost']).mean() > 0.9

@@ -151,3 +151,59 @@ def test_native_ply_writer_bytes_equal_reference_format(tmp_path):
     t_ref = time.perf_counter() - t0
     assert out.read_text() == "\n".join(lines) + "\n"
     assert t_native < t_ref
+
+
+@pytest.mark.parametrize('n', [0, 1, 63, 64, 65, 100003])
+def test_parallel_ply_writer_is_order_and_byte_exact(tmp_path, n):
+    """The writer formats runs of vertices on all host threads and writes the runs in order: for any count (fewer
+    vertices than threads, ragged last run, several 4M-vertex rounds are covered by the run arithmetic) the file equals
+    the sequential formatting, including huge magnitudes that overflow the per-vertex reservation, inf and NaN."""
+    rng = np.random.default_rng(n)
+    pts = rng.normal(size=(n, 3)) * rng.choice([1e-3, 1.0, 1e4], size=(n, 1))
+    if n > 10:
+        pts[3] = [1e300, -1e300, 1e-300]
+        pts[4] = [np.inf, -np.inf, np.nan]
+        pts[5] = [-0.0, 0.4999995, -0.0000005]
+    col = rng.integers(0, 256, size=(n, 3)).astype(np.uint8)
+    out = tmp_path / 'p.ply'
+    save_ply(pts, col, str(out))
+    body = out.read_bytes().split(b'end_header\n', 1)[1]
+    exp = ''.join('%.6f %.6f %.6f %d %d %d\n' % (*p, *c) for p, c in zip(pts.tolist(), col.tolist())).encode()
+    assert body == exp
+
+
+def test_oracle_extension_definitions_on_ground_truth():
+    """CPU sanity of the two EXTENSION definitions in oracle/dense_oracle.c (no dackey-wav counterpart): exact depth maps
+    are geometrically consistent in the sources that see the point and propose (almost) themselves; corrupted depths
+    are rejected / corrected by the proposals."""
+    from b200dense.engine import kinv32
+    from b200dense.scenes import make_scene
+    from oracle import oracle as orc
+    sc = make_scene('wavy', 5, 120, 90, seed=12)
+    ref, src = 2, [1, 3, 0, 4]
+    R = [sc.poses[i][0] for i in range(5)]
+    t = [sc.poses[i][1] for i in range(5)]
+    cams = orc.Cams(sc.K, kinv32(sc.K), R[ref], t[ref], [R[i] for i in src], [t[i] for i in src])
+    d_ref = sc.depth_gt[ref].copy()
+    d_ref[30:50, 40:80] *= 1.2
+    cnt = orc.geo_consistency(d_ref, [sc.depth_gt[i] for i in src], cams, 1.0, 0.01)
+    assert cnt[30:50, 40:80].max() == 0 and (cnt[5:25, 40:80] >= 3).mean() > 0.9
+    assert set(np.unique(cnt)) <= {0.0, 1.0, 2.0, 3.0, 4.0}
+    H, W = d_ref.shape
+    n_ref = np.zeros((H, W, 3), np.float32)
+    n_ref[..., 2] = -1
+    n_src = np.zeros((H, W, 3), np.float32)
+    n_src[..., 0] = 1
+    dmin, dmax = sc.depth_range
+    cd, cn, allow = orc.viewprop_candidates(d_ref, n_ref, sc.depth_gt[src[0]], n_src, 0, cams, dmin, dmax)
+    inner = allow[30:50, 40:80]
+    assert inner.mean() > 0.9
+    # the proposal pulls the corrupted block back towards the true surface (nearest-pixel lookup: not exactly)
+    err_before = np.abs(d_ref - sc.depth_gt[ref])[30:50, 40:80][inner]
+    err_after = np.abs(cd - sc.depth_gt[ref])[30:50, 40:80][inner]
+    assert np.median(err_after) < 0.2 * np.median(err_before)
+    # proposed normal = R_ref R_s^T n_s: unit length, and equal to the rotated source normal
+    exp_n = (R[ref] @ R[src[0]].T @ np.array([1.0, 0, 0])).astype(np.float32)
+    assert np.allclose(cn[allow], exp_n, atol=1e-6)
+    # pixels without a proposal keep their hypothesis
+    assert np.array_equal(cd[~allow], d_ref[~allow]) and np.array_equal(cn[~allow], n_ref[~allow])

@@ -30,7 +30,7 @@ def test_percentile_matches_numpy(n):
     rng = np.random.default_rng(n)
     v = np.sort(rng.normal(size=n) ** 2)
     for q in (95, 50, 1, 99.5):
-        assert _percentile_linear(torch.from_numpy(v), q) == float(np.percentile(v, q))
+        assert float(_percentile_linear(torch.from_numpy(v), q)) == float(np.percentile(v, q))
 
 
 @pytest.mark.parametrize('n,seed', [(3, 0), (10, 1), (4999, 2), (60000, 3)])
