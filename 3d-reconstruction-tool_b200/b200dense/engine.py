@@ -293,7 +293,7 @@ class DenseEngine:
         return float(v.value)
 
     def sweep_fallbacks(self, reset: bool = False) -> int:
-        """(warp, neighbour) evaluations of the bounded plane sweep redone with the exact chains (synchronises)."""
+        """Outputs of the bounded plane sweep redone with the exact chains since the last reset (synchronises)."""
         n = C.c_uint64(0)
         _cabi.check(self.lib.b200d_sweep_fallbacks(C.byref(n), 1 if reset else 0))
         return int(n.value)

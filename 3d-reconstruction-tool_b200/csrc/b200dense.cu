@@ -388,6 +388,7 @@ int setup_eval(Evaluator &ev, const float *d_ref, const float *const *d_src, con
     NccArgs &a = ev.a;
     a.n_src = cams->n_src; a.H = H; a.W = W; a.mean1 = sc.mean1; a.var1 = sc.var1; a.valid = sc.valid; a.cand = sc.cand;
     a.color = -1;
+    a.smap = sc.smap; a.rpad = sc.rpad; a.map_stride = sc.map_stride; a.Wp = sc.Wp; a.pad = (patch / 2) % 4;
     return B200D_OK;
 }
 
@@ -652,8 +653,10 @@ int b200d_plane_sweep(const float *d_ref, const float *const *d_nbr, const b200d
     a.cand = nullptr;
     a.thresh = thresh; a.n_planes = D; a.depths = d_depths;
     if (thresh > 1e-3f && thresh < 1e3f) {                    // quick comparison bounds (sweep_over, sweep_decide_bounded)
-        a.t_lo = (float)((0.999 * thresh) * (0.999 * thresh));
-        a.t_hi = (float)((1.001 * thresh) * (1.001 * thresh));
+        // margin 1e-5 on the threshold: the computed ncc = fl(cov / fl(sqrt(x))) is within (1 +- 4u) of cov / sqrt(x)
+        // and the squared comparison adds 2u, so any margin above ~3e-7 makes the quick decision imply the exact one
+        a.t_lo = (float)(((1.0 - 1e-5) * thresh) * ((1.0 - 1e-5) * thresh));
+        a.t_hi = (float)(((1.0 + 1e-5) * thresh) * ((1.0 + 1e-5) * thresh));
     }
     a.conf = d_conf; a.idx = d_idx; a.depth_map = d_depth_map; a.ncc = d_ncc;
     // PARITY: separable sums + rigorous bound decide `ncc > thresh`, undecided warps redo the exact chains (bit-exact

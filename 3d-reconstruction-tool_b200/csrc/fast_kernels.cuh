@@ -160,9 +160,9 @@ __device__ __forceinline__ void hphase(const float *__restrict__ s_s, const floa
         load_row<NL>(s_s + row * RWP + grp * PX, sv);
         load_row<NL>(s_r + row * RWP + grp * PX, rv);
 #pragma unroll
-        for (int j = 0; j < NL; ++j) {
-            s2[j] = sv[j] * sv[j];                                           // same products as the exact chains
-            rs[j] = rv[j] * sv[j];
+        for (int j = 0; j < NL; j += 2) {                                    // same products as the exact chains (FMUL2)
+            mul2(s2[j], s2[j + 1], sv[j], sv[j + 1], sv[j], sv[j + 1]);
+            mul2(rs[j], rs[j + 1], rv[j], rv[j + 1], sv[j], sv[j + 1]);
         }
         float4 *o = reinterpret_cast<float4 *>(s_h + row * TW + grp * PX);
         o[0] = hsum4<K, NL>(sv);
@@ -171,22 +171,43 @@ __device__ __forceinline__ void hphase(const float *__restrict__ s_s, const floa
     }
 }
 
-// V phase: K+1 rows of one channel for this thread's PX x QY outputs; result scaled by 1/K^2.
+// packed fp32x2 helpers for the V phase: the two halves of an LDS.128 are natural register pairs
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
+    return a;
+}
+__device__ __forceinline__ void mul2_store(float &lo, float &hi, unsigned long long a, unsigned long long w2) {
+    asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(w2));
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a));
+}
+
+// V phase: K+1 rows of one channel for this thread's PX x QY outputs; result scaled by 1/K^2.  FADD2 / FMUL2: half the
+// issue slots of the scalar form, same roundings (each half is one IEEE-RN operation).
 template <int K>
 __device__ __forceinline__ void vphase(const float *__restrict__ h, int tx, int ty, float (&o)[QY][PX]) {
     static_assert(QY == 2 && PX == 4, "thread tile is 4 x 2");
     constexpr float w = 1.0f / (float)(K * K);
     constexpr int RS = TW / 4;
     const float4 *p = reinterpret_cast<const float4 *>(h + (ty * QY) * TW + tx * PX);
-    float4 c = p[RS];
+    float4 t = p[RS];
+    unsigned long long c0 = pack2(t.x, t.y), c1 = pack2(t.z, t.w);
 #pragma unroll
     for (int i = 2; i < K; ++i) {
-        const float4 t = p[i * RS];
-        c.x += t.x; c.y += t.y; c.z += t.z; c.w += t.w;                      // rows 1..K-1 are shared by both outputs
+        t = p[i * RS];
+        c0 = add2(c0, pack2(t.x, t.y));                                       // rows 1..K-1 are shared by both outputs
+        c1 = add2(c1, pack2(t.z, t.w));
     }
     const float4 a0 = p[0], ak = p[K * RS];
-    o[0][0] = (c.x + a0.x) * w; o[0][1] = (c.y + a0.y) * w; o[0][2] = (c.z + a0.z) * w; o[0][3] = (c.w + a0.w) * w;
-    o[1][0] = (c.x + ak.x) * w; o[1][1] = (c.y + ak.y) * w; o[1][2] = (c.z + ak.z) * w; o[1][3] = (c.w + ak.w) * w;
+    const unsigned long long w2 = pack2(w, w);
+    mul2_store(o[0][0], o[0][1], add2(c0, pack2(a0.x, a0.y)), w2);
+    mul2_store(o[0][2], o[0][3], add2(c1, pack2(a0.z, a0.w)), w2);
+    mul2_store(o[1][0], o[1][1], add2(c0, pack2(ak.x, ak.y)), w2);
+    mul2_store(o[1][2], o[1][3], add2(c1, pack2(ak.z, ak.w)), w2);
 }
 
 // ------------------------------------------------------------------------------------------------ bounded decision
@@ -197,42 +218,83 @@ __device__ __forceinline__ void vphase(const float *__restrict__ h, int tx, int 
 //   chain   acc = fma(x_i, w, acc), K^2 steps:      |chain - w sum x_i|  <= gamma_{K^2} * w sum |x_i|
 //   fast    (tree sum of the same terms) * w:       |fast  - w sum x_i|  <= gamma_{2K}  * w sum |x_i|
 //   (the terms x_i are identical in both paths: s_i, fl(s_i*s_i), fl(r_i*s_i))
-// so with C = (K^2 + 2K + 8) u * 1.5 (50 % safety on top of the slack of 8 u):
-//   |m2 - m2~| <= es  = C/2 (1 + a2~)            since  mean|s| <= (1 + mean s^2)/2, mean s^2 <= a2~ (1 + gamma)
+// With C = (K^2 + 2K + 3) u * 1.02 (the 3 u and the 2 % absorb second-order terms, the approximate square root and the
+// roundings of the bound arithmetic itself), q = sqrt(a2~), and Br >= mean r^2 (Br = (var1 + m1^2)(1 + 1e-4)), by
+// Cauchy-Schwarz (mean|s| <= sqrt(mean s^2), mean|r s| <= sqrt(mean r^2 mean s^2), |m2~| <= q (1 + 1e-5)):
+//   |m2 - m2~| <= es  = C q
 //   |a2 - a2~| <= ess = C a2~
-//   |ar - ar~| <= ers = C/2 (Br + a2~)           since  |r s| <= (r^2 + s^2)/2,  Br >= mean r^2  (Br = (var1 + m1^2)(1+1e-4))
-// and through  var2 = fl(a2 - fl(m2 m2)),  cov = fl(ar - fl(m1 m2)),  x = fl(fl(var1 var2) + 1e-8):
-//   |var2 - var2~| <= ev = ess + (2|m2~| + es) es + 4.1u (a2~ + m2~^2)
-//   |cov  - cov~ | <= ec = ers + |m1| es + 4.1u (|ar~| + |m1 m2~|)
-//   |x    - x~   | <= ex = |var1| ev + 4.1u (|x~| + 2e-8)
-// The reference's comparison is then implied by the quick test of the exact kernel (sweep_over: margins 0.1 % on the
-// threshold, four orders above the rounding of sqrt / division) evaluated at the worst corner of the box
-// [cov~ -+ ec] x [x~ -+ ex].  NaN anywhere fails every comparison -> undecided -> exact path.
-// Returns 1 = over, 0 = not over, 2 = undecided.
+//   |ar - ar~| <= ers = C sqrt(Br) q
+// and through  var2 = fl(a2 - fl(m2 m2)),  cov = fl(ar - fl(m1 m2)),  x = fl(fl(var1 var2) + 1e-8), with U4 = 4.1 u:
+//   |var2 - var2~| <= ess + (2|m2~| + es) es + U4 (a2~ + m2~^2)   <=  ev = (3.001 C + 2.01 U4) a2~
+//   |cov  - cov~ | <= ers + |m1| es + U4 (|ar~| + |m1 m2~|)       <=  ec = q * ce,   ce = (C + 1.001 U4)(sqrt(Br) + |m1|)
+//   |x    - x~   | <= ex = |var1| ev + U4 (|x~| + 2e-8)
+// Every bound scales with the signal: an all-zero window (samples outside the source image) has q = 0 and exact sums in
+// both paths, and is decided.  The reference's comparison is then implied by the quick test of the exact kernel
+// (sweep_over: margins 1e-5 on the threshold, ~30x the rounding of sqrt / division) evaluated at the worst
+// corner of the box [cov~ -+ ec] x [x~ -+ ex].  NaN anywhere fails every comparison -> undecided -> exact path.
+// `ce` is the per-output constant above.  Returns 1 = over, 0 = not over, 2 = undecided.
 template <int K>
-__device__ __forceinline__ int sweep_decide_bounded(float m2, float a2, float ar, float m1, float v1, float br, float t_lo,
+struct Bound {
+    static constexpr float U = 5.9604645e-8f;
+    static constexpr float C = (float)(K * K + 2 * K + 3) * U * 1.02f;
+    static constexpr float U4 = 4.1f * U;
+    static constexpr float CE = C + 1.001f * U4;
+    static constexpr float E1 = 3.001f * C + 2.01f * U4;
+};
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+template <int K>
+__device__ __forceinline__ int sweep_decide_bounded(float m2, float a2, float ar, float m1, float v1, float ce, float t_lo,
                                                     float t_hi) {
-    constexpr float U = 5.9604645e-8f;
-    constexpr float C = (float)(K * K + 2 * K + 8) * U * 1.5f;
-    constexpr float U4 = 4.1f * U;
-    const float m2sq = m2 * m2, m1m2 = m1 * m2;
-    const float v2 = a2 - m2sq;
-    const float cov = ar - m1m2;
-    const float x = v1 * v2 + 1e-8f;
-    const float es = (0.5f * C) * (a2 + 1.0f);
-    const float ess = C * a2;
-    const float ers = (0.5f * C) * (br + a2);
-    const float ev = fmaf(U4, a2 + m2sq, fmaf(fmaf(2.0f, fabsf(m2), es), es, ess));
-    const float ec = fmaf(U4, fabsf(ar) + fabsf(m1m2), fmaf(fabsf(m1), es, ers));
-    const float ex = fmaf(fabsf(v1), ev, U4 * (fabsf(x) + 2e-8f));
+    using B = Bound<K>;
+    const float q = sqrt_approx(a2);
+    const float v2 = fmaf(-m2, m2, a2);
+    const float cov = fmaf(-m1, m2, ar);
+    const float x = fmaf(v1, v2, 1e-8f);
+    const float ev = B::E1 * a2;
+    const float ex = fmaf(fabsf(v1), ev, fmaf(B::U4, fabsf(x), 2e-8f * B::U4));
+    const float ec = ce * q;
     const float c_lo = cov - ec, c_hi = cov + ec, x_lo = x - ex, x_hi = x + ex;
     const bool sure_t = (c_lo > 0.0f) & (x_lo > 0.0f) & (c_lo * c_lo > x_hi * t_hi);
     const bool sure_f = (c_hi <= 0.0f) | ((x_lo > 0.0f) & (c_hi * c_hi < x_lo * t_lo));
     return sure_t ? 1 : (sure_f ? 0 : 2);
 }
 
-// hybrid sweep: number of (warp, neighbour) evaluations redone with the exact chains (b200d_sweep_fallbacks); the
-// denominator -- live warps x neighbours x planes -- is known on the host, so the common path carries no atomic
+// The reference's chains for ONE output (gx, gy), read straight from the TMA sources in global memory (L2-resident: the
+// sampling kernel has just written them).  Same taps, same row-major order, same products as box_sums; taps outside the
+// image contribute an exact fma(0, w, acc) = acc, like the zero-filled TMA window.  Rare path, kept out of line.
+template <int K>
+__device__ __noinline__ void exact_one_global(const float *__restrict__ smap, const float *__restrict__ rpad, int Wp, int pad,
+                                              int W, int H, int gx, int gy, float *out3) {
+    constexpr int HALF = K / 2;
+    constexpr float w = 1.0f / (float)(K * K);
+    float as = 0.0f, ass = 0.0f, ars = 0.0f;
+#pragma unroll 1
+    for (int i = 0; i < K; ++i) {
+        const int yy = gy + i - HALF;
+        const bool rowok = (unsigned)yy < (unsigned)H;
+        const size_t ro = (size_t)(rowok ? yy : 0) * Wp + pad;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int xx = gx + j - HALF;
+            const bool ok = rowok & ((unsigned)xx < (unsigned)W);
+            const float sv = ok ? smap[ro + xx] : 0.0f;
+            const float rv = ok ? rpad[ro + xx] : 0.0f;
+            as = fma_(sv, w, as);
+            ass = fma_(mul(sv, sv), w, ass);
+            ars = fma_(mul(rv, sv), w, ars);
+        }
+    }
+    out3[0] = as; out3[1] = ass; out3[2] = ars;
+}
+
+// hybrid sweep: number of outputs redone with the exact chains (b200d_sweep_fallbacks); the denominator -- valid
+// in-image outputs x neighbours x planes -- is known to the host, so the common path carries no atomic
 __device__ unsigned long long g_sweep_fallbacks;
 
 // ------------------------------------------------------------------------------------------------ NCC kernel
@@ -291,13 +353,13 @@ __global__ void __launch_bounds__(NT, B200D_SEP_MIN_BLOCKS) ncc_sep_kernel(const
             v1[q][p] = in ? __ldg(a.var1 + g) : 0.0f;
             // validity bits of outputs outside the image stay 0: they never count and never need the exact path
             vb[q] |= (in ? (unsigned)__ldg(a.valid + g) : 0u) << (8 * p);
-            br[q][p] = (v1[q][p] + m1[q][p] * m1[q][p]) * 1.0001f;
+            br[q][p] = Bound<K>::CE * (sqrtf((v1[q][p] + m1[q][p] * m1[q][p]) * 1.0001f) * 1.0001f + fabsf(m1[q][p]));
             total[q][p] = 0.0f;
         }
     }
 
-    const int lane = tid & 31;
     const bool warp_live = y0 + (tid / 32) * (32 / NTX) * QY < H;
+    unsigned long long und_all = 0;                        // A_HYBRID: bit 8 s + (q PX + p) = output still undecided
     mbar_wait(&bar[2], 0);
     for (int s = 0; s < S; ++s) {
         const int st = s & 1;
@@ -312,9 +374,11 @@ __global__ void __launch_bounds__(NT, B200D_SEP_MIN_BLOCKS) ncc_sep_kernel(const
             vphase<K>(s_h + 2 * FG::HCH, tx, ty, ars);
         }
         if (ARITH == A_HYBRID) {
-            // ---- plane sweep, parity results: bounded decision, exact redo of the warps that hold an undecided output
-            unsigned over = 0, und = 0;
+            // ---- plane sweep, parity results: bounded decision now; the outputs it cannot decide are remembered (one
+            // bit per neighbour x output) and redone with the exact chains after the neighbour loop, so no warp waits
+            // at the stage barriers for another warp's exact work
             if (warp_live) {
+                unsigned und = 0;
 #pragma unroll
                 for (int q = 0; q < QY; ++q)
 #pragma unroll
@@ -323,31 +387,10 @@ __global__ void __launch_bounds__(NT, B200D_SEP_MIN_BLOCKS) ncc_sep_kernel(const
                         const int dcs = (a.t_lo > 0.0f) ? sweep_decide_bounded<K>(as[q][p], ass[q][p], ars[q][p], m1[q][p],
                                                                                   v1[q][p], br[q][p], a.t_lo, a.t_hi)
                                                         : 2;
-                        over |= (dcs == 1 ? 1u : 0u) << (q * PX + p);
+                        if ((dcs == 1) & valid) total[q][p] = add(total[q][p], 1.0f);          // :303-304
                         und |= ((dcs == 2) & valid ? 1u : 0u) << (q * PX + p);
                     }
-                if (__any_sync(0xffffffffu, und != 0)) {
-                    box_sums<K>(sb, s_r, tx, ty, as, ass, ars);               // the reference's chains, tile still resident
-                    over = 0;
-#pragma unroll
-                    for (int q = 0; q < QY; ++q)
-#pragma unroll
-                        for (int p = 0; p < PX; ++p) {
-                            const float m2 = as[q][p];
-                            const float v2 = sub(ass[q][p], mul(m2, m2));
-                            const float cov = sub(ars[q][p], mul(m1[q][p], m2));
-                            const float x = add(mul(v1[q][p], v2), 1e-8f);
-                            over |= (sweep_over(cov, x, a.thresh, a.t_lo, a.t_hi) ? 1u : 0u) << (q * PX + p);
-                        }
-                    if (lane == 0) atomicAdd(&g_sweep_fallbacks, 1ull);
-                }
-#pragma unroll
-                for (int q = 0; q < QY; ++q)
-#pragma unroll
-                    for (int p = 0; p < PX; ++p) {
-                        const bool valid = (vb[q] >> (8 * p + s)) & 1u;
-                        if (((over >> (q * PX + p)) & 1u) && valid) total[q][p] = add(total[q][p], 1.0f);   // :303-304
-                    }
+                und_all |= (unsigned long long)und << (8 * s);
             }
         } else if (warp_live) {
             // ---- B200D_FAST: same formulas, MUFU reciprocal / rsqrt, no rounding discipline
@@ -382,6 +425,32 @@ __global__ void __launch_bounds__(NT, B200D_SEP_MIN_BLOCKS) ncc_sep_kernel(const
             mbar_expect_tx(&bar[st], G::tile_bytes);
             tma_load_2d(s_r + (1 + st) * BUF, &a.tm_s[s + 2], &bar[st], cx, cy);
         }
+    }
+
+    // ---- A_HYBRID: exact redo of the undecided (neighbour, output) pairs, one output at a time
+    if (ARITH == A_HYBRID) {
+        unsigned extra = 0, redone = 0;                    // 4-bit counters per output
+        while (und_all) {
+            const int b = __ffsll((long long)und_all) - 1;
+            und_all &= und_all - 1;
+            const int s = b >> 3, o = b & 7;
+            const int gx = x0 + tx * PX + (o % PX), gy = y0 + ty * QY + (o / PX);
+            float e3[3];
+            exact_one_global<K>(a.smap + (size_t)s * a.map_stride, a.rpad, a.Wp, a.pad, W, H, gx, gy, e3);
+            const size_t g = (size_t)gy * W + gx;
+            const float m1v = __ldg(a.mean1 + g), v1v = __ldg(a.var1 + g);
+            const float v2 = sub(e3[1], mul(e3[0], e3[0]));
+            const float cov = sub(e3[2], mul(m1v, e3[0]));
+            const float x = add(mul(v1v, v2), 1e-8f);
+            if (sweep_over(cov, x, a.thresh, a.t_lo, a.t_hi)) extra += 1u << (4 * o);          // valid by construction
+            ++redone;
+        }
+        const unsigned wsum = __reduce_add_sync(0xffffffffu, redone);
+        if ((tid & 31) == 0 && wsum) atomicAdd(&g_sweep_fallbacks, (unsigned long long)wsum);
+#pragma unroll
+        for (int q = 0; q < QY; ++q)
+#pragma unroll
+            for (int p = 0; p < PX; ++p) total[q][p] = add(total[q][p], (float)((extra >> (4 * (q * PX + p))) & 15u));
     }
 
     // ---- epilogue (same rules as ncc_kernel)

@@ -58,11 +58,15 @@ struct NccArgs {
     uint32_t view_id, eval_id;
     // N_SWEEP
     float thresh;
-    float t_lo, t_hi;                        // (0.999 thresh)^2, (1.001 thresh)^2 ; 0 = always take the exact comparison
+    float t_lo, t_hi;                        // ((1 -+ 1e-5) thresh)^2 ; 0 = always take the exact comparison
     int plane, n_planes;
     const float *depths;
     float *conf, *depth_map, *ncc;
     int32_t *idx;
+    // raw views of the TMA sources (bounded plane sweep: exact redo of single outputs straight from L2)
+    const float *smap, *rpad;                // sampled maps / reference copy: pixel x at column x + pad, row pitch Wp
+    size_t map_stride;
+    int Wp, pad;
 };
 
 template <int K>
@@ -192,8 +196,9 @@ __device__ __forceinline__ void box_sums(const float *__restrict__ s_s, const fl
 }
 
 // Plane sweep: `ncc > thresh` for ncc = cov / sqrt(x), x = var1*var2 + 1e-8 (dense_stereo.py:303, 344-345), decided
-// without the square root and the division whenever cov^2 is clearly off thresh^2 * x (t_lo = (0.999 thresh)^2,
-// t_hi = (1.001 thresh)^2: margins four orders above the rounding errors involved); only the sliver around the
+// without the square root and the division whenever cov^2 is clearly off thresh^2 * x (t_lo = ((1 - 1e-5) thresh)^2,
+// t_hi = ((1 + 1e-5) thresh)^2: the computed quotient is within (1 +- 4u) of cov / sqrt(x) and the squared comparison
+// adds 2u, so the 1e-5 margin is ~30x what the implication needs); only the sliver around the
 // threshold, zero / negative / non-finite x, and a disabled quick test (t_lo == 0) take the exact path.
 __device__ __forceinline__ bool sweep_over(float cov, float x, float thresh, float t_lo, float t_hi) {
     const float c2 = mul(cov, cov);
@@ -329,7 +334,7 @@ __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_
                 if (MODE == N_SWEEP || MODE == N_SWEEP_DUMP) {
                     // ncc = cov / sqrt(var1*var2 + 1e-8) (dense_stereo.py:344-345) is only ever compared with the
                     // threshold (:303).  The comparison is decided without the square root and the division whenever
-                    // cov^2 is clearly off thresh^2 * x (0.1 % margins, four orders above the rounding errors involved);
+                    // cov^2 is clearly off thresh^2 * x (1e-5 margins, ~30x the rounding errors involved: sweep_over);
                     // only the sliver around the threshold (and zero / negative / non-finite x) takes the exact path.
                     const float x = add(mul(v1v, v2), 1e-8f);
                     bool over;

@@ -170,8 +170,8 @@ B200D_API int b200d_plane_sweep(const float *d_ref, const float *const *d_nbr, c
                                 float *d_depth_map, float *d_conf, int32_t *d_idx, float *d_ncc, void *d_scratch,
                                 void *stream);
 
-/* Diagnostic (synchronises the device): number of (warp, neighbour) evaluations of the B200D_PARITY plane sweep whose
- * bounded decision was inconclusive and which were redone with the reference's chains, since the last reset. */
+/* Diagnostic (synchronises the device): number of (pixel, neighbour, plane) outputs of the B200D_PARITY plane sweep
+ * whose bounded decision was inconclusive and which were redone with the reference's chains, since the last reset. */
 B200D_API int b200d_sweep_fallbacks(uint64_t *count, int reset);
 
 /* Replaces the per-view body of PatchMatchMVS._fuse_depth_maps (mvs_patchmatch.py:545-565, mode 0:
