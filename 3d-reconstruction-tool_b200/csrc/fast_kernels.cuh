@@ -216,9 +216,10 @@ __device__ __forceinline__ void vphase(const float *__restrict__ h, int tx, int 
 //
 // Notation: u = 2^-24, w = fl(1/K^2) (same constant in both paths), gamma_n = n u / (1 - n u).
 //   chain   acc = fma(x_i, w, acc), K^2 steps:      |chain - w sum x_i|  <= gamma_{K^2} * w sum |x_i|
-//   fast    (tree sum of the same terms) * w:       |fast  - w sum x_i|  <= gamma_{2K}  * w sum |x_i|
+//   fast    (tree sum of the same terms) * w:       |fast  - w sum x_i|  <= gamma_{2K-1} * w sum |x_i|
+//           (longest path: K - 3 additions in hsum4, K - 1 in vphase, one multiplication; 2K - 1 covers K = 3, 5 too)
 //   (the terms x_i are identical in both paths: s_i, fl(s_i*s_i), fl(r_i*s_i))
-// With C = (K^2 + 2K + 3) u * 1.02 (the 3 u and the 2 % absorb second-order terms, the approximate square root and the
+// With C = (K^2 + 2K + 1) u * 1.02 (the 2 u and the 2 % absorb second-order terms, the approximate square root and the
 // roundings of the bound arithmetic itself), q = sqrt(a2~), and Br >= mean r^2 (Br = (var1 + m1^2)(1 + 1e-4)), by
 // Cauchy-Schwarz (mean|s| <= sqrt(mean s^2), mean|r s| <= sqrt(mean r^2 mean s^2), |m2~| <= q (1 + 1e-5)):
 //   |m2 - m2~| <= es  = C q
@@ -236,7 +237,7 @@ __device__ __forceinline__ void vphase(const float *__restrict__ h, int tx, int 
 template <int K>
 struct Bound {
     static constexpr float U = 5.9604645e-8f;
-    static constexpr float C = (float)(K * K + 2 * K + 3) * U * 1.02f;
+    static constexpr float C = (float)(K * K + 2 * K + 1) * U * 1.02f;   // chain K^2 roundings + fast path <= 2K - 1
     static constexpr float U4 = 4.1f * U;
     static constexpr float CE = C + 1.001f * U4;
     static constexpr float E1 = 3.001f * C + 2.01f * U4;
@@ -274,20 +275,38 @@ __device__ __noinline__ void exact_one_global(const float *__restrict__ smap, co
     constexpr int HALF = K / 2;
     constexpr float w = 1.0f / (float)(K * K);
     float as = 0.0f, ass = 0.0f, ars = 0.0f;
+    if (gx >= HALF && gx + HALF < W && gy >= HALF && gy + HALF < H) {
+        // window wholly inside the image (the usual case): no per-tap bounds tests
+        const float *ps = smap + (size_t)(gy - HALF) * Wp + pad + gx - HALF;
+        const float *pr = rpad + (size_t)(gy - HALF) * Wp + pad + gx - HALF;
 #pragma unroll 1
-    for (int i = 0; i < K; ++i) {
-        const int yy = gy + i - HALF;
-        const bool rowok = (unsigned)yy < (unsigned)H;
-        const size_t ro = (size_t)(rowok ? yy : 0) * Wp + pad;
+        for (int i = 0; i < K; ++i) {
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const int xx = gx + j - HALF;
-            const bool ok = rowok & ((unsigned)xx < (unsigned)W);
-            const float sv = ok ? smap[ro + xx] : 0.0f;
-            const float rv = ok ? rpad[ro + xx] : 0.0f;
-            as = fma_(sv, w, as);
-            ass = fma_(mul(sv, sv), w, ass);
-            ars = fma_(mul(rv, sv), w, ars);
+            for (int j = 0; j < K; ++j) {
+                const float sv = ps[j], rv = pr[j];
+                as = fma_(sv, w, as);
+                ass = fma_(mul(sv, sv), w, ass);
+                ars = fma_(mul(rv, sv), w, ars);
+            }
+            ps += Wp;
+            pr += Wp;
+        }
+    } else {
+#pragma unroll 1
+        for (int i = 0; i < K; ++i) {
+            const int yy = gy + i - HALF;
+            const bool rowok = (unsigned)yy < (unsigned)H;
+            const size_t ro = (size_t)(rowok ? yy : 0) * Wp + pad;
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const int xx = gx + j - HALF;
+                const bool ok = rowok & ((unsigned)xx < (unsigned)W);
+                const float sv = ok ? smap[ro + xx] : 0.0f;
+                const float rv = ok ? rpad[ro + xx] : 0.0f;
+                as = fma_(sv, w, as);
+                ass = fma_(mul(sv, sv), w, ass);
+                ars = fma_(mul(rv, sv), w, ars);
+            }
         }
     }
     out3[0] = as; out3[1] = ass; out3[2] = ars;
@@ -353,7 +372,7 @@ __global__ void __launch_bounds__(NT, B200D_SEP_MIN_BLOCKS) ncc_sep_kernel(const
             v1[q][p] = in ? __ldg(a.var1 + g) : 0.0f;
             // validity bits of outputs outside the image stay 0: they never count and never need the exact path
             vb[q] |= (in ? (unsigned)__ldg(a.valid + g) : 0u) << (8 * p);
-            br[q][p] = Bound<K>::CE * (sqrtf((v1[q][p] + m1[q][p] * m1[q][p]) * 1.0001f) * 1.0001f + fabsf(m1[q][p]));
+            br[q][p] = Bound<K>::CE * (sqrt_approx((v1[q][p] + m1[q][p] * m1[q][p]) * 1.0001f) * 1.0001f + fabsf(m1[q][p]));
             total[q][p] = 0.0f;
         }
     }

@@ -278,8 +278,14 @@ __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_
         const int st = s & 1;
         mbar_wait(&bar[st], (s >> 1) & 1);
         // a warp owns QY*2 consecutive tile rows; in the bottom row of tiles some warps lie wholly below the image:
-        // they keep taking part in the stage hand-over but have nothing to sum or to select
-        if (warp_live) box_sums<K>(s_r + (1 + st) * BUF, (MODE == N_STATS) ? s_r + BUF : s_r, tx, ty, as, ass, ars);
+        // they keep taking part in the stage hand-over but have nothing to sum or to select.  The same holds for a
+        // (warp, source) none of whose 256 outputs has a valid projection into this source (image borders, hypotheses
+        // far off the surface): every use of the NCC below is gated by `valid` (mvs_patchmatch.py:383-384, 530-532;
+        // dense_stereo.py:303), so the chains would be computed and thrown away -- skip them (bit-identical results)
+        bool src_live = warp_live;
+        if (MODE != N_STATS && MODE != N_SWEEP_DUMP)
+            src_live = __any_sync(0xffffffffu, (((vb[0] | vb[1]) >> s) & 0x01010101u) != 0u) && warp_live;
+        if (src_live) box_sums<K>(s_r + (1 + st) * BUF, (MODE == N_STATS) ? s_r + BUF : s_r, tx, ty, as, ass, ars);
         if (MODE == N_STATS) break;
         if (s + 2 < S) {
             // release the stage: one arrival per warp; the producer thread refills it once all 8 arrived
@@ -295,7 +301,7 @@ __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_
         // all of them through the branch-free fast paths (eight independent MUFU + FMA chains the compiler interleaves),
         // then the rare untrusted ones (negative / non-finite / near-denormal operands) again with the IEEE intrinsics
         float nccv[QY][PX];
-        if (warp_live && MODE != N_STATS && MODE != N_SWEEP && MODE != N_SWEEP_DUMP) {
+        if (src_live && MODE != N_STATS && MODE != N_SWEEP && MODE != N_SWEEP_DUMP) {
             unsigned bad = 0;
 #pragma unroll
             for (int q = 0; q < QY; ++q)
@@ -321,7 +327,7 @@ __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_
                         }
             }
         }
-        if (warp_live)
+        if (src_live)
 #pragma unroll
         for (int q = 0; q < QY; ++q)
 #pragma unroll

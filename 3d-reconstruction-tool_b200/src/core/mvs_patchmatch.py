@@ -131,15 +131,18 @@ class PatchMatchMVS:
             self._dev_gray[idx] = (id(g), t)
         return t
 
-    def _stage_images(self, images: Dict, indices) -> Dict[int, "torch.cuda.Event"]:
+    def _stage_images(self, images: Dict, indices, ready: Dict = None) -> Dict[int, "torch.cuda.Event"]:
         """Upload (and, on the device-prepare path, resize + gray) the listed images on the copy stream, in order of
         first use, and return one event per image.  A job on another stream waits for the events of the images it
         reads before it launches anything, so no kernel can read an image whose upload / prepare kernel is still in
-        flight on a different stream; the first views start while later images are still crossing PCIe."""
+        flight on a different stream.  Called incrementally (`ready` carries over): reconstruct() stages the images of
+        view j right before it enqueues view j, so the GPU already works on the first views while the host is still
+        pushing later photographs through PCIe (uploads from the caller's pageable arrays block the host thread)."""
         eng = self.engine
-        ready: Dict[int, torch.cuda.Event] = {}
         copy_stream = eng.copy_stream()
-        copy_stream.wait_stream(torch.cuda.current_stream(eng.device))
+        if ready is None:
+            ready = {}
+            copy_stream.wait_stream(torch.cuda.current_stream(eng.device))
         with torch.cuda.stream(copy_stream):
             for i in indices:
                 if i in ready:
@@ -196,28 +199,46 @@ class PatchMatchMVS:
         eng = self.engine
         dev = eng.device
         Kinv = np.linalg.inv(self.K_scaled)
-        plan = []
-        for pos in range(rank, n_cams, ws):
-            ref_idx = cam_indices[pos]
-            src_indices = self._select_source_views(ref_idx, cam_indices, poses, k=self.num_src_views)
-            if len(src_indices) < 2:
-                print(f"  [{pos+1}/{n_cams}] Cam {ref_idx}: skipped (not enough neighbors)")
-                continue
-            plan.append((pos, ref_idx, src_indices))
-        need = [i for _, r, src in plan for i in [r] + list(src)]
-        ready = self._stage_images(proc_images, need)
+        ready = self._stage_images(proc_images, [])             # opens the copy stream; images follow view by view
         # host-drawn random numbers must be consumed in view order -> one view at a time in that mode
         in_flight = 1 if self.rng == 'torch' else self.views_in_flight
+        mine = [(pos, cam_indices[pos]) for pos in range(rank, n_cams, ws)]
         if self.schedule == 'viewprop':
+            plan = []
+            for pos, ref_idx in mine:
+                src_indices = self._select_source_views(ref_idx, cam_indices, poses, k=self.num_src_views)
+                if len(src_indices) < 2:
+                    print(f"  [{pos+1}/{n_cams}] Cam {ref_idx}: skipped (not enough neighbors)")
+                    continue
+                plan.append((pos, ref_idx, src_indices))
             maps = self._run_viewprop(plan, cam_indices, proc_images, poses, ready, in_flight)
         else:
-            def view_job(ref_idx, src_indices):
+            # source selection, image staging and kernel launches of view j+1 all happen on the host while the GPU
+            # works on view j: nothing but the first view's preparation is exposed
+            def view_job(pos, ref_idx):
                 def job(slot):
+                    h0 = time.perf_counter()
+                    src_indices = self._select_source_views(ref_idx, cam_indices, poses, k=self.num_src_views)
+                    if len(src_indices) < 2:
+                        print(f"  [{pos+1}/{n_cams}] Cam {ref_idx}: skipped (not enough neighbors)")
+                        return None
+                    h1 = time.perf_counter()
+                    self._stage_images(proc_images, [ref_idx] + list(src_indices), ready)
                     self._wait_images(ready, [ref_idx] + list(src_indices))
-                    return self._patchmatch_device(ref_idx, src_indices, proc_images, poses, slot=slot)
+                    h2 = time.perf_counter()
+                    out = self._patchmatch_device(ref_idx, src_indices, proc_images, poses, slot=slot)
+                    h3 = time.perf_counter()
+                    tm['host_select_s'] = tm.get('host_select_s', 0.0) + (h1 - h0)
+                    tm['host_stage_upload_s'] = tm.get('host_stage_upload_s', 0.0) + (h2 - h1)
+                    tm['host_enqueue_s'] = tm.get('host_enqueue_s', 0.0) + (h3 - h2)
+                    # the fusion needs depth + confidence only; at 3840x2160 a normal map is 100 MB per view, which a
+                    # 200-view job would otherwise hold until the end (released in stream order: allocator-safe)
+                    out.pop('normal', None)
+                    return src_indices, out
                 return job
-            results = eng.run_views([view_job(r, s) for _, r, s in plan], in_flight)
-            maps = {ref_idx: out for (_, ref_idx, _), out in zip(plan, results)}
+            results = eng.run_views([view_job(pos, r) for pos, r in mine], in_flight)
+            plan = [(pos, r, res[0]) for (pos, r), res in zip(mine, results) if res is not None]
+            maps = {r: res[1] for (_, r), res in zip(mine, results) if res is not None}
         if self.consistency == 'geometric':
             self._geometric_filter(plan, cam_indices, proc_images, poses, maps)
 
@@ -274,7 +295,8 @@ class PatchMatchMVS:
         elif self.device_postfilter:
             from b200dense.postfilter import filter_points
             fp, fc = filter_points(pts_d, col_d)                 # same selection and order as _filter_points
-            points, colors = eng.to_host([fp, fc])
+            # one-off size: a pageable download beats page-locking a fresh staging buffer (~1 GB/s to pin)
+            points, colors = fp.cpu().numpy(), fc.cpu().numpy()
             print(f"  After filtering: {len(points):,}")
         else:
             points, colors = self._filter_points(pts_d.cpu().numpy(), col_d.cpu().numpy())
@@ -329,6 +351,7 @@ class PatchMatchMVS:
 
         def pm_stage(r, src, it_begin, it_end, stage):
             def job(slot):
+                self._stage_images(images, [r] + list(src), ready)
                 self._wait_images(ready, [r] + list(src))
                 return eng.pm_view(self._gray_on_device(images, r), [self._gray_on_device(images, i) for i in src],
                                    self._camera_block(r, src, poses), self.patch_size, iters, self.num_samples,
@@ -392,15 +415,21 @@ class PatchMatchMVS:
     def _select_source_views(self, ref_idx: int, all_indices: List[int], poses: Dict[int, CameraPose],
                              k: int = 4) -> List[int]:
         """Top-k by baseline * (1 - |angle - 20|/60) for 5 < angle < 60 degrees, else 0; ties keep
-        index order (stable sort) -- reference :193-223."""
-        c0 = poses[ref_idx].center
-        d0 = poses[ref_idx].R[2, :]
+        index order (stable sort) -- reference :193-223.  Camera centres and viewing directions are computed once per
+        pose set (the reference recomputes `-R.T @ t` for every pair; same values, 200 views = 40,000 pairs)."""
+        cache = getattr(self, '_pose_cache', None)
+        if cache is None or cache[0] is not poses or cache[1] != len(poses):
+            cache = (poses, len(poses), {i: poses[i].center for i in poses}, {i: poses[i].R[2, :] for i in poses})
+            self._pose_cache = cache
+        centers, dirs = cache[2], cache[3]
+        c0 = centers[ref_idx]
+        d0 = dirs[ref_idx]
         scored = []
         for idx in all_indices:
             if idx == ref_idx:
                 continue
-            baseline = np.linalg.norm(poses[idx].center - c0)
-            angle = np.degrees(np.arccos(np.clip(np.dot(d0, poses[idx].R[2, :]), -1, 1)))
+            baseline = np.linalg.norm(centers[idx] - c0)
+            angle = np.degrees(np.arccos(np.clip(np.dot(d0, dirs[idx]), -1, 1)))
             scored.append((idx, baseline * (1 - abs(angle - 20) / 60) if 5 < angle < 60 else 0))
         scored.sort(key=lambda p: p[1], reverse=True)
         return [idx for idx, _ in scored[:k]]
