@@ -9,7 +9,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
+#include <thread>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -851,9 +853,13 @@ int b200d_write_ply_ascii(const char *path, const double *points, const uint8_t 
     if (!f) return fail(B200D_ERR_ARG, "cannot open output file");
     fprintf(f, "ply\nformat ascii 1.0\nelement vertex %lld\nproperty float x\nproperty float y\nproperty float z\n"
                "property uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n", (long long)n);
+    // Threads: the cores this process may run on (affinity mask), not OMP_NUM_THREADS -- launchers such as torchrun
+    // export OMP_NUM_THREADS=1 for every rank, yet only rank 0 writes the cloud.  B200D_PLY_THREADS overrides.
     int T = 1;
 #ifdef _OPENMP
-    T = omp_get_max_threads();
+    T = (int)std::thread::hardware_concurrency();
+    if (const char *e = getenv("B200D_PLY_THREADS")) T = atoi(e);
+    if (T < 1) T = 1;
     if (T > 64) T = 64;
 #endif
     const int64_t BLOCK = 1 << 22;                       // vertices formatted per round (bounds the staging memory)

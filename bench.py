@@ -639,7 +639,23 @@ def reconstruct_leg(a, dev, world, barrier, max_over_ranks, n_views=16):
         barrier()
     dt = max_over_ranks(time.perf_counter() - t0)
     tm = dict(pm.last_timings)
-    return {'value': n_views / dt, 'unit': UNIT, 'views': n_views, 'seconds': dt,
+    # the same through the view-propagation extension: all views in lock step, depth + normal maps all-gathered after
+    # every iteration (NCCL at N>1), one proposal evaluation per source view
+    with quiet():
+        pv = PatchMatchMVS(cam, scale=1.0, patch_size=a.patch, num_iterations=a.iters, num_samples=a.samples, min_views=3,
+                           num_src_views=a.src, seed=1234, arith=a.arith, device=dev, schedule='viewprop')
+        pv.reconstruct(images, poses, sparse_points=sparse)
+        barrier()
+        t0 = time.perf_counter()
+        vpts, _ = pv.reconstruct(images, poses, sparse_points=sparse)
+        barrier()
+    dtv = max_over_ranks(time.perf_counter() - t0)
+    viewprop = {'value': n_views / dtv, 'unit': UNIT, 'seconds': dtv, 'points_out': int(len(vpts)),
+                'evaluations_per_view': a.iters * (2 + a.samples + a.src) + 1,
+                'exchange': f'{a.iters} all-gathers of depth + normal maps of all {n_views} views',
+                'note': 'EXTENSION schedule=\'viewprop\' (no dackey-wav counterpart); bit-equal to its NumPy-on-oracle definition '
+                        '(tests/test_gpu_viewprop.py), 2-rank result == 1-rank result (tests/test_gpu_multi.py)'}
+    return {'value': n_views / dt, 'unit': UNIT, 'views': n_views, 'seconds': dt, 'viewprop_schedule': viewprop,
             'h2d_bytes_per_step': n_views * a.height * a.width * 3, 'd2h_bytes_per_step': int(len(pts)) * 27,
             'points_out': int(len(pts)), 'phases_rank0_s': tm,
             'api': 'core.mvs_patchmatch.PatchMatchMVS.reconstruct(images, poses, sparse_points): host BGR photographs in, '

@@ -35,7 +35,9 @@ def _run(rank, ws, port, q, mode='photometric'):
     cam = Camera(K=sc.K.copy(), dist=np.zeros(5))
     poses = {i: CameraPose(R=sc.poses[i][0], t=sc.poses[i][1]) for i in sc.poses}
     pm = PatchMatchMVS(cam, scale=1.0, patch_size=7, num_iterations=2, num_samples=2, min_views=2, seed=5,
-                       device=f'cuda:{rank}', consistency=mode, geo_min_views=1, geo_rel_thresh=0.02, geo_px_thresh=2.0)
+                       device=f'cuda:{rank}', consistency='geometric' if mode == 'geometric' else 'photometric',
+                       geo_min_views=1, geo_rel_thresh=0.02, geo_px_thresh=2.0,
+                       schedule='viewprop' if mode == 'viewprop' else 'reference')
     sparse = np.stack([np.zeros(20), np.zeros(20), np.linspace(4.0, 6.0, 20)], axis=1)
     p, c = pm.reconstruct(sc.images, poses, sparse_points=sparse)
     q.put((rank, p, c))
@@ -44,9 +46,10 @@ def _run(rank, ws, port, q, mode='photometric'):
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize('mode', ['photometric', 'geometric'])
+@pytest.mark.parametrize('mode', ['photometric', 'geometric', 'viewprop'])
 def test_two_rank_reconstruct_equals_single_rank(mode):
-    """'geometric' additionally exercises the NCCL all-gather of the depth maps."""
+    """'geometric' additionally exercises the NCCL all-gather of the depth maps, 'viewprop' the per-iteration all-gather of
+    depth AND normal maps (the proposals are evaluated from snapshots, so the result must not depend on the sharding)."""
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     ctx = mp.get_context('spawn')
