@@ -92,6 +92,21 @@ def quiet():
     return contextlib.redirect_stdout(io.StringIO())
 
 
+def config_dict(a, world):
+    """The `config` object of the JSON line -- the same for the b200 arm and the reference (CPU) arm, which times a
+    bounded sample of this workload (its sample is described in `cpu_baseline.sample`, not here)."""
+    ns = max(1, min(a.streams, a.views_per_gpu))
+    return {'workload': workload_name(a), 'views_per_step_per_gpu': a.views_per_gpu,
+            'arithmetic': 'parity (bit-exact vs oracle)' if a.arith == 'parity'
+                          else 'B200D_FAST (opt-in; NOT bit-exact, fails the parity gates: see fast_mode)',
+            'rng': 'philox4x32-10 in-kernel (production generator: checked statistically and for determinism; '
+                   'the bit-exact parity tests inject the reference\'s own draws, incl. at this 1600x1200 shape)',
+            'l2': 'flushed between timed steps (512 MiB write)', 'views_in_flight': ns,
+            'consistency': a.consistency,
+            'parallelism': f'view-sharded dp{world}' + (', fused clouds gathered to rank 0 every step (NCCL p2p '
+                                                        'into the final buffer)' if world > 1 else '')}
+
+
 def scene_for(a, ref_views, device, extra_views=()):
     """Poses for all 64 views; pixels only for the views this rank touches (+ `extra_views` and their sources)."""
     from b200dense.scenes import make_scene
@@ -212,7 +227,7 @@ def run_reference(a):
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps,
         'warmup': a.warmup, 'ms_per_step': dt / a.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name(a), 'sample': sample},
+        'config': config_dict(a, max(1, a.gpus)),
         'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
         'reference_pytorch_cpu': REFERENCE_PYTORCH_CPU,
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
@@ -599,15 +614,7 @@ def main():
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
             'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': workload_name(a), 'views_per_step_per_gpu': V,
-                       'arithmetic': 'parity (bit-exact vs oracle)' if a.arith == 'parity'
-                                     else 'B200D_FAST (opt-in; NOT bit-exact, fails the parity gates: see fast_mode)',
-                       'rng': 'philox4x32-10 in-kernel (production generator: checked statistically and for determinism; '
-                              'the bit-exact parity tests inject the reference\'s own draws, incl. at this 1600x1200 shape)',
-                       'l2': 'flushed between timed steps (512 MiB write)', 'views_in_flight': NS,
-                       'consistency': a.consistency,
-                       'parallelism': f'view-sharded dp{world}' + (', fused clouds gathered to rank 0 every step (NCCL p2p '
-                                                                   'into the final buffer)' if world > 1 else '')},
+            'config': config_dict(a, world),
             'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches,
             'gather_check': gather_check, 'exchange': exchange, 'e2e_reconstruct': e2e_rec, 'plane_sweep': sweep,
             'fast_mode': fast_mode}))
