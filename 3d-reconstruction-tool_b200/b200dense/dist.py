@@ -5,7 +5,12 @@ reference view independently, so the path shards by views with no da
 
     rank r computes views[r::world]        (round-robin keeps turntable neighbours on different GPUs)
 
-Only two exchanges exist:
+Exchanges:
+  * `peer_cloud` / `peer_fence` -- the preferred cloud gather on NVLink boxes: rank 0's output buffers are symmetric
+    (peer-mapped) memory, and every rank's back-projection kernel stores its points STRAIGHT INTO rank 0's final cloud
+    at the view's global offset, over NVLink -- compute and transfer are one kernel, there is no send / receive step,
+    only a fence.  Falls back to the NCCL point-to-point gather below where symmetric memory is unavailable.
+Besides, two exchanges exist:
   * `gather_point_clouds` -- the fused points/colours of all views are collected on rank 0 in sorted
     view order, which is the order the reference's `np.vstack` over its depth-map dict produces
     (mvs_patchmatch.py:544-570, dense_stereo.py:138-139).  Variable-length: one all-gather of the
@@ -15,7 +20,8 @@ Only two exchanges exist:
 """
 from __future__ import annotations
 
-from typing import Dict, List, Sequence, Tuple
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -81,6 +87,68 @@ def gather_into(counts: Sequence[int], local: Dict[int, Tuple[torch.Tensor, torc
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
+
+
+class _PeerCloud:
+    """Symmetric (peer-mapped) cloud buffer on every rank of the job; rank 0's copy is the destination."""
+
+    def __init__(self, device: torch.device):
+        self.device, self.cap, self.raw, self.handle = device, 0, None, None
+
+    def ensure(self, n: int) -> None:
+        if n <= self.cap:
+            return
+        import torch.distributed._symmetric_memory as symm_mem
+        cap = max(int(n * 1.25) + 1024, 1 << 20)
+        # one allocation, one rendezvous: 24 bytes of coordinates + 3 bytes of colour per point (+ slack for alignment)
+        self.raw = symm_mem.empty(cap * 32, dtype=torch.uint8, device=self.device)
+        self.handle = symm_mem.rendezvous(self.raw, dist.group.WORLD)
+        self.cap = cap
+
+    def views(self, n: int, of_rank: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        raw = self.raw if of_rank == dist.get_rank() else self.handle.get_buffer(of_rank, (self.cap * 32,), torch.uint8)
+        pts = raw[:self.cap * 24].view(torch.float64).view(self.cap, 3)
+        col = raw[self.cap * 24:self.cap * 27].view(self.cap, 3)
+        return pts[:n], col[:n]
+
+
+_PEER: Dict[torch.device, _PeerCloud] = {}
+_PEER_DISABLED = [False]
+
+
+def peer_cloud(device: torch.device, n_points: int) -> Optional[Tuple[torch.Tensor, torch.Tensor]]:
+    """COLLECTIVE.  (points (n,3) f64, colors (n,3) u8) views of RANK 0's cloud buffer, writable from this rank's kernels
+    (peer memory over NVLink; on rank 0 its own memory).  Every rank back-projects each of its views into the slice at the
+    view's global offset and then calls `peer_fence`; after the fence rank 0 holds the complete cloud in the reference's
+    order -- no packing, no send / receive.  Returns None (on every rank alike) when the job is single-rank, not on NCCL,
+    empty, disabled with B200D_NO_PEER_GATHER=1, or when symmetric memory cannot be set up: callers then use
+    `gather_into`.  The buffer persists and grows geometrically (a rendezvous costs ~0.1-2 s)."""
+    rank, ws = world()
+    if ws == 1 or n_points <= 0 or _PEER_DISABLED[0] or os.environ.get('B200D_NO_PEER_GATHER'):
+        return None
+    if dist.get_backend() != 'nccl' or device.type != 'cuda':
+        return None
+    pc = _PEER.setdefault(device, _PeerCloud(device))
+    if n_points > pc.cap:                                   # same decision on every rank: n_points and cap history agree
+        ok = 1
+        try:
+            pc.ensure(n_points)
+        except Exception:                                   # noqa: BLE001  (driver / fabric without peer mapping)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            _PEER_DISABLED[0] = True
+            _PEER.pop(device, None)
+            return None
+    return pc.views(n_points, 0)
+
+
+def peer_fence(device: torch.device) -> None:
+    """COLLECTIVE.  All kernels this rank enqueued on its current stream have completed (their stores into rank 0's
+    buffer are performed), and every rank has reached this point: rank 0 may read the cloud."""
+    torch.cuda.current_stream(device).synchronize()
+    dist.barrier()
 
 
 def gather_point_clouds(views: Sequence[int], local: Dict[int, Tuple[torch.Tensor, torch.Tensor]],

@@ -258,14 +258,18 @@ class PatchMatchMVS:
         all_counts = bdist.exchange_counts(n_cams, local_counts, dev)
         offs = np.concatenate([[0], np.cumsum(all_counts)]).astype(np.int64)
         total = int(offs[-1])
-        if rank == 0:
+        dest = bdist.peer_cloud(dev, total)                      # rank 0's cloud, peer-mapped over NVLink (or None)
+        if dest is not None:
+            buf_p, buf_c = dest                                 # every rank writes at the views' GLOBAL offsets
+            base = {pos: int(offs[pos]) for pos, _, _ in plan}
+        elif rank == 0:
             buf_p = torch.empty((total, 3), dtype=torch.float64, device=dev)
             buf_c = torch.empty((total, 3), dtype=torch.uint8, device=dev)
             base = {pos: int(offs[pos]) for pos, _, _ in plan}
         else:
-            mine = int(sum(local_counts.values()))
-            buf_p = torch.empty((mine, 3), dtype=torch.float64, device=dev)
-            buf_c = torch.empty((mine, 3), dtype=torch.uint8, device=dev)
+            mine_n = int(sum(local_counts.values()))
+            buf_p = torch.empty((mine_n, 3), dtype=torch.float64, device=dev)
+            buf_c = torch.empty((mine_n, 3), dtype=torch.uint8, device=dev)
             run, base = 0, {}
             for pos, _, _ in plan:
                 base[pos] = run
@@ -282,7 +286,12 @@ class PatchMatchMVS:
                                  poses[ref_idx].R, poses[ref_idx].t, float(self.min_views), 0, points=sl[0],
                                  colors=sl[1], count=dummy, sync=False)
             local[pos] = sl
-        bdist.gather_into(all_counts, local, buf_p if rank == 0 else None, buf_c if rank == 0 else None)
+        if dest is not None:
+            bdist.peer_fence(dev)                               # the back-projection kernels WERE the transfer
+            tm['gather'] = 'peer stores into rank 0 (symmetric memory over NVLink)'
+        else:
+            bdist.gather_into(all_counts, local, buf_p if rank == 0 else None, buf_c if rank == 0 else None)
+            tm['gather'] = 'NCCL point-to-point into the final slices' if ws > 1 else 'single rank'
         tm['fusion_gather_s'] = time.time() - t1
         if rank != 0:
             torch.cuda.current_stream(dev).synchronize()

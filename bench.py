@@ -355,35 +355,74 @@ def main():
         return ev, checked
 
     big = {}
+    cnt_d = torch.zeros(V, dtype=torch.int64, device=dev)
+    dummy = torch.zeros(1, dtype=torch.int64, device=dev)
+    dev_t = torch.device(dev)
+
+    def count_job(j, r, arith):
+        pj = pm_job(r, arith)
+
+        def job(slot):
+            o = pj(slot)
+            return eng.mask_count(o['depth'], o['confidence'], 3.0, 0, cnt_d[j:j + 1], slot=slot)
+        return job
 
     def step(arith=ARITH):
+        if world == 1:
+            if geometric:
+                eng.run_views([pm_job(r, arith) for r in ref_views], NS)
+                exchange_and_filter()
+                return [fuse(r) for r in ref_views]
+            return eng.run_views([view_job(r, arith) for r in ref_views], NS)
+        # N > 1 -- the job's only exchange under reference semantics: the fused clouds of all ranks' views on rank 0 in
+        # sorted-view order (mvs_patchmatch.py:544-570).  Masks are counted on the device, the counts exchanged once, and
+        # then every rank back-projects each view STRAIGHT INTO rank 0's cloud at its global offset (peer memory over
+        # NVLink: the back-projection kernel is the transfer); NCCL point-to-point into the final slices is the fallback.
         if geometric:
             eng.run_views([pm_job(r, arith) for r in ref_views], NS)
             exchange_and_filter()
-            res = [fuse(r) for r in ref_views]
+            for j, r in enumerate(ref_views):
+                eng.mask_count(outs[r]['depth'], outs[r]['confidence'], 3.0, 0, cnt_d[j:j + 1])
         else:
-            res = eng.run_views([view_job(r, arith) for r in ref_views], NS)
-        if world > 1:
-            # the job's only exchange under reference semantics: fused clouds of all ranks' views -> rank 0, sorted-view
-            # order (mvs_patchmatch.py:544-570).  Counts once, then NCCL p2p straight into the final slices.
-            cnts = torch.cat([c for _, _, c in res]).cpu().tolist()
-            counts = bdist.exchange_counts(len(all_views), {pos_of[r]: m for r, m in zip(ref_views, cnts)}, torch.device(dev))
-            offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
-            total = int(offs[-1])
+            eng.run_views([count_job(j, r, arith) for j, r in enumerate(ref_views)], NS)
+        cnts = cnt_d.cpu().tolist()
+        counts = bdist.exchange_counts(len(all_views), {pos_of[r]: m for r, m in zip(ref_views, cnts)}, dev_t)
+        offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        total = int(offs[-1])
+        dest = bdist.peer_cloud(dev_t, total)
+
+        def bp(r, pts, cols):
+            o = outs[r]
+            eng.mask_backproject(o['depth'], o['confidence'], d_bgr[r], Kinv64, poses[r].R, poses[r].t, 3.0, 0,
+                                 points=pts, colors=cols, count=dummy, sync=False)
+        if dest is not None:
+            for r, m in zip(ref_views, cnts):
+                o = int(offs[pos_of[r]])
+                if m:
+                    bp(r, dest[0][o:o + m], dest[1][o:o + m])
+            bdist.peer_fence(dev_t)
+            state['gather'] = 'peer stores into rank 0 (symmetric memory over NVLink)'
+            if rank == 0:
+                state.update(points=dest[0], colors=dest[1], counts=counts, offs=offs)
+        else:
+            state['gather'] = 'NCCL point-to-point into the final slices'
             if rank == 0:
                 if 'p' not in big or big['p'].shape[0] < total:
                     big['p'] = torch.empty((total + (total >> 3), 3), dtype=torch.float64, device=dev)
                     big['c'] = torch.empty((total + (total >> 3), 3), dtype=torch.uint8, device=dev)
                 fp, fc = big['p'][:total], big['c'][:total]
-                for r, m in zip(ref_views, cnts):                           # own views: device-to-device into place
+                for r, m in zip(ref_views, cnts):                           # own views: straight into place
                     o = int(offs[pos_of[r]])
-                    fp[o:o + m].copy_(pts_buf[r][:m])
-                    fc[o:o + m].copy_(col_buf[r][:m])
+                    if m:
+                        bp(r, fp[o:o + m], fc[o:o + m])
                 bdist.gather_into(counts, {}, fp, fc)
                 state.update(points=fp, colors=fc, counts=counts, offs=offs)
             else:
+                for r, m in zip(ref_views, cnts):
+                    if m:
+                        bp(r, pts_buf[r][:m], col_buf[r][:m])
                 bdist.gather_into(counts, {pos_of[r]: (pts_buf[r][:m], col_buf[r][:m]) for r, m in zip(ref_views, cnts)})
-        return res
+        return None
 
     def barrier():
         if world > 1:
@@ -438,13 +477,15 @@ def main():
                 m = int(cnt.item())
                 o = int(state['offs'][pos_of[r]])
                 own = ref_views[0]
-                m0, o0 = int(state['counts'][pos_of[own]]), int(state['offs'][pos_of[own]])
-                ok = (m == int(state['counts'][pos_of[r]])
+                pm_job(own, ARITH)(0)
+                p0, c0, cnt0 = fuse(own)
+                m0, o0 = int(cnt0.item()), int(state['offs'][pos_of[own]])
+                ok = (m == int(state['counts'][pos_of[r]]) and m0 == int(state['counts'][pos_of[own]])
                       and torch.equal(state['points'][o:o + m], p[:m]) and torch.equal(state['colors'][o:o + m], c[:m])
-                      and torch.equal(state['points'][o0:o0 + m0], pts_buf[own][:m0])
+                      and torch.equal(state['points'][o0:o0 + m0], p0[:m0]) and torch.equal(state['colors'][o0:o0 + m0], c0[:m0])
                       and int(state['points'].shape[0]) == int(sum(state['counts'])))
                 gather_check = {'ok': bool(ok), 'points': int(state['points'].shape[0]), 'views': len(all_views),
-                                'checked_view': int(r), 'owner_rank': 1, 'slice_points': m,
+                                'checked_view': int(r), 'owner_rank': 1, 'slice_points': m, 'gather': state.get('gather'),
                                 'how': 'rank 0 recomputed a view owned by rank 1 (same seed / view id) and compared its fused '
                                        'slice of the gathered cloud bit for bit (points f64 + colours); own slice and total '
                                        'count checked too'}
