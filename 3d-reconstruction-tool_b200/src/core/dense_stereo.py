@@ -226,6 +226,46 @@ class DenseStereoReconstructor:
         out = self._sweep_device(ref_idx, neighbor_indices, processed, poses, depth_min, depth_max)
         return out['depth_map'].cpu().numpy(), out['confidence'].cpu().numpy(), processed[ref_idx]['color']
 
+    def compute_depth_maps(self, processed: Dict, poses: Dict[int, CameraPose], ref_indices: List[int],
+                           neighbors: Dict[int, List[int]], depth_min: float,
+                           depth_max: float) -> Dict[int, Tuple[np.ndarray, np.ndarray]]:
+        """Batch form of `_compute_depth_map_gpu`: host grays in, host (depth_map, confidence) out, for many reference
+        views at once.  Every distinct gray is uploaded once per call on the copy stream (a view waits only for its own
+        images), the views run `views_in_flight` at a time on separate streams, and each view's maps come back through
+        pooled page-locked staging on its own stream, so copies overlap the other views' kernels.  Same results as the
+        per-view call (the kernels are deterministic)."""
+        from b200dense.engine import PINNED
+        eng = self.engine
+        self._dev_gray.clear()                               # every call uploads what it reads
+        ready = {}
+        copy_stream = eng.copy_stream()
+        copy_stream.wait_stream(torch.cuda.current_stream(eng.device))
+        with torch.cuda.stream(copy_stream):
+            for r in ref_indices:
+                for i in [r] + list(neighbors[r]):
+                    if i not in ready:
+                        self._gray_on_device(processed, i)
+                        ready[i] = torch.cuda.Event()
+                        ready[i].record(copy_stream)
+        jobs = []
+        for r in ref_indices:
+            def job(slot, r=r):
+                st = torch.cuda.current_stream(eng.device)
+                for i in [r] + list(neighbors[r]):
+                    st.wait_event(ready[i])
+                out = self._sweep_device(r, neighbors[r], processed, poses, depth_min, depth_max, slot=slot)
+                host = []
+                for key in ('depth_map', 'confidence'):
+                    h = PINNED.take(out[key].shape, out[key].dtype)
+                    h.copy_(out[key], non_blocking=True)
+                    host.append(h)
+                return out, host
+            jobs.append(job)
+        results = eng.run_views(jobs, self.views_in_flight)
+        torch.cuda.current_stream().synchronize()
+        self._dev_gray.clear()
+        return {r: (PINNED.as_numpy(host[0]), PINNED.as_numpy(host[1])) for r, (_, host) in zip(ref_indices, results)}
+
     def _sweep_device(self, ref_idx, neighbor_indices, processed, poses, depth_min, depth_max, slot: int = 0) -> dict:
         from b200dense.engine import kinv32, make_cams
         eng = self.engine

@@ -790,20 +790,25 @@ def sweep_leg(a, eng, dev, rank, world, barrier, max_over_ranks, fp32_peak):
     processed = {i: {'gray': pinned[i].numpy(), 'color': None, 'shape': (Hs, Ws)} for i in nb_views}
     poses = {i: CameraPose(R=scs.poses[i][0], t=scs.poses[i][1]) for i in scs.poses}
 
-    def e2e_view(r):
-        ds._dev_gray.clear()                               # every view uploads its 7 grays again
-        return ds._compute_depth_map_gpu(r, nbs_of(r), processed, poses, scs.depth_range[0], scs.depth_range[1])
-    e2e_view(3)
+    nbr_of = {r: nbs_of(r) for r in refs_s}
+    ds.views_in_flight = a.sweep_streams
+
+    def e2e_step():
+        maps = ds.compute_depth_maps(processed, poses, refs_s, nbr_of, scs.depth_range[0], scs.depth_range[1])
+        assert len(maps) == len(refs_s) and maps[refs_s[0]][0].shape == (Hs, Ws)
+    e2e_step()
     barrier()
     t0 = time.perf_counter()
-    for r in refs_s[:2]:
-        dm, cf, _ = e2e_view(r)
+    for _ in range(2):
+        e2e_step()
     barrier()
     dt = max_over_ranks(time.perf_counter() - t0)
-    sweep['e2e'] = {'value': world * 2 * Hs * Ws * D / dt / 1e9, 'unit': 'Gpix*planes/s',
-                    'h2d_bytes_per_step': 7 * Hs * Ws * 4, 'd2h_bytes_per_step': 2 * Hs * Ws * 4,
-                    'api': 'core.dense_stereo.DenseStereoReconstructor._compute_depth_map_gpu (host grays in, host depth map + '
-                           'confidence out, one view per step, views serialised)'}
+    n_img = len({i for r in refs_s for i in [r] + nbr_of[r]})
+    sweep['e2e'] = {'value': world * 2 * len(refs_s) * Hs * Ws * D / dt / 1e9, 'unit': 'Gpix*planes/s',
+                    'h2d_bytes_per_step': n_img * Hs * Ws * 4, 'd2h_bytes_per_step': len(refs_s) * 2 * Hs * Ws * 4,
+                    'api': 'core.dense_stereo.DenseStereoReconstructor.compute_depth_maps (batch form of _compute_depth_map_gpu: '
+                           'pinned host grays in, every distinct image uploaded once per step, host depth map + confidence out; '
+                           f'{len(refs_s)} views per step, {a.sweep_streams} in flight)'}
     # CPU arm of this metric: BASELINE configs[0] in full through the port (5 views 640x480, 64 planes, 7x7, N=4)
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         from oracle import oracle as orc

@@ -175,3 +175,25 @@ def test_pm_view_rejects_bad_depth_range(engine):
     for dmin, dmax in ((0.0, 1.0), (-1.0, 1.0), (2.0, 1.0), (1.0, float('inf')), (float('nan'), 1.0)):
         with pytest.raises(B200DenseError):
             engine.pm_view(x, [x, x], cams, 5, 1, 1, dmin, dmax)
+
+
+def test_stereo_compute_depth_maps_equals_per_view_calls():
+    """Batch form of `_compute_depth_map_gpu` (uploads on the copy stream, views in flight, pinned downloads) gives the
+    per-view call's maps bit for bit."""
+    import contextlib
+    import io
+    from b200dense.scenes import gray_f32, make_scene
+    sc = make_scene('wavy', 7, 200, 150, seed=8, arc_deg=5.0)
+    cam = Camera(K=sc.K.copy(), dist=np.zeros(5))
+    poses = {i: CameraPose(R=sc.poses[i][0], t=sc.poses[i][1]) for i in sc.poses}
+    gray = gray_f32(sc)
+    processed = {i: {'gray': gray[i], 'color': sc.images[i]['image'], 'shape': gray[i].shape} for i in range(7)}
+    with contextlib.redirect_stdout(io.StringIO()):
+        ds = DenseStereoReconstructor(cam, scale=1.0, num_depths=24, patch_size=7)
+    refs = [1, 2, 3, 4, 5]
+    nbrs = {r: ds._find_neighbors(r, sorted(poses), poses, k=4) for r in refs}
+    dmin, dmax = sc.depth_range
+    batch = ds.compute_depth_maps(processed, poses, refs, nbrs, dmin, dmax)
+    for r in refs:
+        d, c, _ = ds._compute_depth_map_gpu(r, nbrs[r], processed, poses, dmin, dmax)
+        assert np.array_equal(batch[r][0], d) and np.array_equal(batch[r][1], c)
