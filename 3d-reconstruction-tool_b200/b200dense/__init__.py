@@ -8,4 +8,4 @@ Layout
 
 The reference-facing drop-in classes live in ../src/core (same module names as the reference).
 """
-from ._cabi import B200DenseError, FAST, PARITY, PARITY_CHAINS, LIB_PATH  # noqa: F401
+from ._cabi import B200DenseError, FAST, PARITY, PARITY_CHAINS, PARITY_CHECK, LIB_PATH  # noqa: F401

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 MAX_SRC = 8
-PARITY, FAST, PARITY_CHAINS = 0, 1, 2
+PARITY, FAST, PARITY_CHAINS, PARITY_CHECK = 0, 1, 2, 3
 SCHEDULE_REFERENCE, SCHEDULE_REDBLACK = 0, 1
 STAGE_NO_INIT, STAGE_NO_CONF = 1, 2
 ABI_VERSION = 3
@@ -54,6 +54,7 @@ PROTOTYPES = {
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'b200d_pm_viewprop': (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(Cams), _i, _i, C.POINTER(PmParams), C.POINTER(_vp),
                                     C.POINTER(_vp), _vp, _vp, _vp, _vp, _vp, _vp]),
+    'b200d_sweep_bound_check': (C.c_int, [C.POINTER(C.c_float), _i]),
     'b200d_sweep_fallbacks': (C.c_int, [C.POINTER(C.c_uint64), _i]),
     'b200d_plane_sweep': (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(Cams), C.POINTER(C.c_float), _i, _i, _i, _i, _f, _i,
                                     _vp, _vp, _vp, _vp, _vp, _vp]),

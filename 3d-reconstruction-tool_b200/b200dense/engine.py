@@ -292,6 +292,13 @@ class DenseEngine:
         _cabi.check(self.lib.b200d_measure_fp32_peak(C.byref(v), self._stream()))
         return float(v.value)
 
+    def sweep_bound_check(self, reset: bool = False):
+        """(r_m2, r_a2, r_ar): largest observed |separable sum - chain| / bound since the last reset, from plane sweeps run
+        with arith=PARITY_CHECK (synchronises)."""
+        v = (C.c_float * 3)()
+        _cabi.check(self.lib.b200d_sweep_bound_check(v, 1 if reset else 0))
+        return tuple(float(x) for x in v)
+
     def sweep_fallbacks(self, reset: bool = False) -> int:
         """Outputs of the bounded plane sweep redone with the exact chains since the last reset (synchronises)."""
         n = C.c_uint64(0)

@@ -217,7 +217,7 @@ template <int K, int MODE, int ARITH>
 int launch_sep(const NccArgs &a, cudaStream_t st) {
     static std::atomic<uint64_t> configured{0};
     TRY(ensure_smem(ncc_sep_kernel<K, MODE, ARITH>, configured, FGeo<K>::smem_bytes));
-    ProfScope prof((ARITH == A_FAST ? 10000 : 20000) + MODE * 100 + K, st);
+    ProfScope prof((ARITH == A_FAST ? 10000 : ARITH == A_HYBRID ? 20000 : 30000) + MODE * 100 + K, st);
     const dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, 1);
     ncc_sep_kernel<K, MODE, ARITH><<<grid, NT, FGeo<K>::smem_bytes, st>>>(a);
     return cuda_check(cudaGetLastError(), "ncc_sep_kernel launch");
@@ -371,8 +371,8 @@ int stats_impl(const NccArgs &prepared, int H, int W, int patch, float *mean1, f
 }
 
 int check_arith(int arith) {
-    if (arith != B200D_PARITY && arith != B200D_FAST && arith != B200D_PARITY_CHAINS)
-        return fail(B200D_ERR_ARG, "arith must be B200D_PARITY, B200D_FAST or B200D_PARITY_CHAINS");
+    if (arith != B200D_PARITY && arith != B200D_FAST && arith != B200D_PARITY_CHAINS && arith != B200D_PARITY_CHECK)
+        return fail(B200D_ERR_ARG, "arith must be B200D_PARITY, B200D_FAST, B200D_PARITY_CHAINS or B200D_PARITY_CHECK");
     return B200D_OK;
 }
 
@@ -664,15 +664,29 @@ int b200d_plane_sweep(const float *d_ref, const float *const *d_nbr, const b200d
     // PARITY: separable sums + rigorous bound decide `ncc > thresh`, undecided warps redo the exact chains (bit-exact
     // counts); PARITY_CHAINS: the exact chains everywhere (A/B reference of the former); the NCC dump needs the values
     // themselves, hence the chains.
-    const bool hybrid = arith == B200D_PARITY && !d_ncc && a.t_lo > 0.0f;
+    const bool hybrid = (arith == B200D_PARITY || arith == B200D_PARITY_CHECK) && !d_ncc && a.t_lo > 0.0f;
     for (int d = 0; d < D; ++d) {
         s.plane_depth = depths_host[d];
         a.plane = d;
         TRY((ev.sample<C_PLANE, B_DEPTH>()));
         if (arith == B200D_FAST) TRY((launch_sep_k<N_SWEEP, A_FAST>(patch, a, st)));
+        else if (hybrid && arith == B200D_PARITY_CHECK) TRY((launch_sep_k<N_SWEEP, A_CHECK>(patch, a, st)));
         else if (hybrid) TRY((launch_sep_k<N_SWEEP, A_HYBRID>(patch, a, st)));
         else if (d_ncc) TRY(launch_ncc_k<N_SWEEP_DUMP>(patch, a, st));
         else TRY(launch_ncc_k<N_SWEEP>(patch, a, st));
+    }
+    return B200D_OK;
+}
+
+int b200d_sweep_bound_check(float *ratios3, int reset) {
+    unsigned v[3] = {0, 0, 0};
+    if (ratios3) {
+        CUDA_TRY(cudaMemcpyFromSymbol(v, g_bound_ratio, sizeof(v)));
+        memcpy(ratios3, v, sizeof(v));
+    }
+    if (reset) {
+        v[0] = v[1] = v[2] = 0;
+        CUDA_TRY(cudaMemcpyToSymbol(g_bound_ratio, v, sizeof(v)));
     }
     return B200D_OK;
 }

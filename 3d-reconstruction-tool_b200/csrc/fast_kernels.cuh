@@ -26,7 +26,7 @@
 
 namespace b200d {
 
-enum FastArith { A_FAST = 0, A_HYBRID = 1 };
+enum FastArith { A_FAST = 0, A_HYBRID = 1, A_CHECK = 2 };     // A_CHECK = A_HYBRID + measurement of the bound's slack
 
 // ------------------------------------------------------------------------------------------------ sampling (A_FAST)
 struct FastCams {
@@ -222,12 +222,13 @@ __device__ __forceinline__ void vphase(const float *__restrict__ h, int tx, int 
 // With C = (K^2 + 2K + 1) u * 1.02 (the 2 u and the 2 % absorb second-order terms, the approximate square root and the
 // roundings of the bound arithmetic itself), q = sqrt(a2~), and Br >= mean r^2 (Br = (var1 + m1^2)(1 + 1e-4)), by
 // Cauchy-Schwarz (mean|s| <= sqrt(mean s^2), mean|r s| <= sqrt(mean r^2 mean s^2), |m2~| <= q (1 + 1e-5)):
-//   |m2 - m2~| <= es  = C q
-//   |a2 - a2~| <= ess = C a2~
-//   |ar - ar~| <= ers = C sqrt(Br) q
+//   |m2 - m2~| <= es  = C q + T0
+//   |a2 - a2~| <= ess = C a2~ + T0
+//   |ar - ar~| <= ers = C sqrt(Br) q + T0         (T0 = 1e-42: absolute slack for subnormal results, see Bound)
 // and through  var2 = fl(a2 - fl(m2 m2)),  cov = fl(ar - fl(m1 m2)),  x = fl(fl(var1 var2) + 1e-8), with U4 = 4.1 u:
-//   |var2 - var2~| <= ess + (2|m2~| + es) es + U4 (a2~ + m2~^2)   <=  ev = (3.001 C + 2.01 U4) a2~
-//   |cov  - cov~ | <= ers + |m1| es + U4 (|ar~| + |m1 m2~|)       <=  ec = q * ce,   ce = (C + 1.001 U4)(sqrt(Br) + |m1|)
+//   |var2 - var2~| <= ess + (2|m2~| + es) es + U4 (a2~ + m2~^2)   <=  ev = (3.001 C + 2.01 U4) a2~ + T0 (2|m2~| + 4)
+//   |cov  - cov~ | <= ers + |m1| es + U4 (|ar~| + |m1 m2~|)       <=  ec = q * ce + T0 (|m1| + 4),
+//                                                                       ce = (C + 1.001 U4)(sqrt(Br) + |m1|)
 //   |x    - x~   | <= ex = |var1| ev + U4 (|x~| + 2e-8)
 // Every bound scales with the signal: an all-zero window (samples outside the source image) has q = 0 and exact sums in
 // both paths, and is decided.  The reference's comparison is then implied by the quick test of the exact kernel
@@ -241,6 +242,9 @@ struct Bound {
     static constexpr float U4 = 4.1f * U;
     static constexpr float CE = C + 1.001f * U4;
     static constexpr float E1 = 3.001f * C + 2.01f * U4;
+    // gradual underflow: an operation whose result is subnormal errs by up to 2^-150 ABSOLUTE instead of u relative, so
+    // each of the three sums carries an absolute slack of (K^2 + 2K) 2^-150 < 3e-43 <= T0 on top of the relative bound
+    static constexpr float T0 = 1e-42f;
 };
 
 __device__ __forceinline__ float sqrt_approx(float x) {
@@ -257,9 +261,9 @@ __device__ __forceinline__ int sweep_decide_bounded(float m2, float a2, float ar
     const float v2 = fmaf(-m2, m2, a2);
     const float cov = fmaf(-m1, m2, ar);
     const float x = fmaf(v1, v2, 1e-8f);
-    const float ev = B::E1 * a2;
+    const float ev = fmaf(B::E1, a2, B::T0 * fmaf(2.0f, fabsf(m2), 4.0f));
     const float ex = fmaf(fabsf(v1), ev, fmaf(B::U4, fabsf(x), 2e-8f * B::U4));
-    const float ec = ce * q;
+    const float ec = fmaf(ce, q, B::T0 * (fabsf(m1) + 4.0f));
     const float c_lo = cov - ec, c_hi = cov + ec, x_lo = x - ex, x_hi = x + ex;
     const bool sure_t = (c_lo > 0.0f) & (x_lo > 0.0f) & (c_lo * c_lo > x_hi * t_hi);
     const bool sure_f = (c_hi <= 0.0f) | ((x_lo > 0.0f) & (c_hi * c_hi < x_lo * t_lo));
@@ -312,6 +316,12 @@ __device__ __noinline__ void exact_one_global(const float *__restrict__ smap, co
     out3[0] = as; out3[1] = ass; out3[2] = ars;
 }
 
+// A_CHECK (diagnostic twin of A_HYBRID, b200d_sweep_bound_check): for every output and neighbour the reference's chains are
+// evaluated as well and the observed distance |separable - chain| is divided by the bound the decision relies on; the
+// maxima over everything evaluated (float bit patterns, ratios are >= 0) land here.  A ratio above 1 would falsify the
+// derivation at sweep_decide_bounded; the tests assert <= 1 on textured, flat, dark, denormal, huge and negative images.
+__device__ unsigned g_bound_ratio[3];      // m2, a2 = box(s*s), ar = box(r*s)
+
 // hybrid sweep: number of outputs redone with the exact chains (b200d_sweep_fallbacks); the denominator -- valid
 // in-image outputs x neighbours x planes -- is known to the host, so the common path carries no atomic
 __device__ unsigned long long g_sweep_fallbacks;
@@ -328,6 +338,7 @@ __global__ void __launch_bounds__(NT, B200D_SEP_MIN_BLOCKS) ncc_sep_kernel(const
     using FG = FGeo<K>;
     constexpr int HALF = G::HALF;
     static_assert(ARITH == A_FAST || MODE == N_SWEEP, "the bounded decision exists for the plane sweep only");
+    constexpr bool HYB = ARITH == A_HYBRID || ARITH == A_CHECK;
     extern __shared__ __align__(128) unsigned char sm[];
     constexpr int BUF = G::buf_bytes / sizeof(float);
     float *s_r = reinterpret_cast<float *>(sm);
@@ -392,7 +403,36 @@ __global__ void __launch_bounds__(NT, B200D_SEP_MIN_BLOCKS) ncc_sep_kernel(const
             vphase<K>(s_h + FG::HCH, tx, ty, ass);
             vphase<K>(s_h + 2 * FG::HCH, tx, ty, ars);
         }
-        if (ARITH == A_HYBRID) {
+        if (ARITH == A_CHECK && warp_live) {
+            // diagnostic: observed |separable - chain| over the bound, for the three sums of every output
+            float xs[QY][PX], xss[QY][PX], xrs[QY][PX];
+            box_sums<K>(sb, s_r, tx, ty, xs, xss, xrs);
+            float r0 = 0.0f, r1 = 0.0f, r2 = 0.0f;
+            auto ratio = [](float d, float b) { return d == 0.0f ? 0.0f : (b > 0.0f ? d / b : __int_as_float(0x7f800000)); };
+#pragma unroll
+            for (int q = 0; q < QY; ++q)
+#pragma unroll
+                for (int p = 0; p < PX; ++p) {
+                    if (x0 + tx * PX + p >= W || y0 + ty * QY + q >= H) continue;    // outputs outside the image are never used
+                    const float qq = sqrt_approx(ass[q][p]);
+                    const float sb_ = sqrt_approx((v1[q][p] + m1[q][p] * m1[q][p]) * 1.0001f) * 1.0001f;
+                    r0 = fmaxf(r0, ratio(fabsf(as[q][p] - xs[q][p]), fmaf(Bound<K>::C, qq, Bound<K>::T0)));
+                    r1 = fmaxf(r1, ratio(fabsf(ass[q][p] - xss[q][p]), fmaf(Bound<K>::C, ass[q][p], Bound<K>::T0)));
+                    r2 = fmaxf(r2, ratio(fabsf(ars[q][p] - xrs[q][p]), fmaf(Bound<K>::C * sb_, qq, Bound<K>::T0)));
+                }
+            // NaN inputs give NaN ratios, which fmaxf drops: those outputs are undecided anyway
+            for (int o = 16; o; o >>= 1) {
+                r0 = fmaxf(r0, __shfl_xor_sync(0xffffffffu, r0, o));
+                r1 = fmaxf(r1, __shfl_xor_sync(0xffffffffu, r1, o));
+                r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, o));
+            }
+            if ((tid & 31) == 0) {
+                atomicMax(&g_bound_ratio[0], __float_as_uint(r0));
+                atomicMax(&g_bound_ratio[1], __float_as_uint(r1));
+                atomicMax(&g_bound_ratio[2], __float_as_uint(r2));
+            }
+        }
+        if (HYB) {
             // ---- plane sweep, parity results: bounded decision now; the outputs it cannot decide are remembered (one
             // bit per neighbour x output) and redone with the exact chains after the neighbour loop, so no warp waits
             // at the stage barriers for another warp's exact work
@@ -447,7 +487,7 @@ __global__ void __launch_bounds__(NT, B200D_SEP_MIN_BLOCKS) ncc_sep_kernel(const
     }
 
     // ---- A_HYBRID: exact redo of the undecided (neighbour, output) pairs, one output at a time
-    if (ARITH == A_HYBRID) {
+    if (HYB) {
         unsigned extra = 0, redone = 0;                    // 4-bit counters per output
         while (und_all) {
             const int b = __ffsll((long long)und_all) - 1;

@@ -26,6 +26,9 @@
  *                 reference's chains: same counts / arg-max bit for bit (csrc/fast_kernels.cuh).
  *   B200D_PARITY_CHAINS  same results as B200D_PARITY; the plane sweep evaluates the reference's chains for
  *                 every output (the A/B twin of the bounded decision, used by tests and profiling).
+ *   B200D_PARITY_CHECK   diagnostic twin of B200D_PARITY for the plane sweep: same results, and for every output the
+ *                 observed distance between the separable sums and the reference's chains is compared with the bound
+ *                 the decision relies on (b200d_sweep_bound_check).  Slow; tests only.
  *   B200D_FAST    OPT-IN, NOT BIT-EXACT, never the default: composed reprojection, direct bilinear lookup,
  *                 separable window sums, MUFU reciprocal / rsqrt.  It misses the north_star tolerances wherever a
  *                 patch is flat (var = E[x^2] - E[x]^2 is ill-conditioned) and its agreement with
@@ -57,7 +60,7 @@ typedef enum {
     B200D_ERR_UNSUPPORTED = -3
 } b200d_status;
 
-typedef enum { B200D_PARITY = 0, B200D_FAST = 1, B200D_PARITY_CHAINS = 2 } b200d_arith;
+typedef enum { B200D_PARITY = 0, B200D_FAST = 1, B200D_PARITY_CHAINS = 2, B200D_PARITY_CHECK = 3 } b200d_arith;
 
 /* Camera block, fp32, exactly what the reference uploads per reference view
  * (mvs_patchmatch.py:237-257, dense_stereo.py:232-259): K = K_scaled cast to fp32,
@@ -173,6 +176,11 @@ B200D_API int b200d_plane_sweep(const float *d_ref, const float *const *d_nbr, c
 /* Diagnostic (synchronises the device): number of (pixel, neighbour, plane) outputs of the B200D_PARITY plane sweep
  * whose bounded decision was inconclusive and which were redone with the reference's chains, since the last reset. */
 B200D_API int b200d_sweep_fallbacks(uint64_t *count, int reset);
+
+/* Diagnostic (synchronises the device): after plane sweeps run with B200D_PARITY_CHECK, ratios3 (HOST, 3 floats) receives
+ * the largest observed |separable sum - reference chain| / bound for the three window sums box(s), box(s*s), box(r*s) over
+ * every output evaluated since the last reset.  Values <= 1 confirm the error bound behind the bit-exact decision. */
+B200D_API int b200d_sweep_bound_check(float *ratios3, int reset);
 
 /* Replaces the per-view body of PatchMatchMVS._fuse_depth_maps (mvs_patchmatch.py:545-565, mode 0:
  * valid = conf >= min_conf) and DenseStereoReconstructor._backproject (dense_stereo.py:414-437,
