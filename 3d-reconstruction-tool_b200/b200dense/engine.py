@@ -368,6 +368,63 @@ class DenseEngine:
         self.launches += 2
         return count
 
+    def fuse_to_rank0(self, n_positions: int, items: Sequence[dict], Kinv64: np.ndarray, min_conf: float, mode: int):
+        """Fusion of many views into ONE cloud on rank 0 in view order, with a single host synchronisation.
+
+        `items`: this rank's views, each dict(pos=index in the sorted view list, depth, conf (device maps), bgr=callable
+        returning the device colour image, R, t).  Steps: count every mask on the device (b200d_mask_count) -> read the
+        counts once -> exchange them (one small all-reduce) -> rank 0's cloud is allocated exactly (symmetric memory when
+        the job is multi-GPU: dist.peer_cloud) -> every rank back-projects each view straight into its slice at the
+        view's global offset (over NVLink for ranks > 0: the kernel is the transfer) -> fence.  Fallback without peer
+        memory: NCCL point-to-point into the final slices (dist.gather_into).  Returns (points, colors, counts, how) on
+        rank 0 and (None, None, counts, how) elsewhere; `counts` has one entry per position."""
+        from . import dist as bdist
+        rank, ws = bdist.world()
+        dev = self.device
+        counts_d = torch.zeros(max(1, len(items)), dtype=torch.int64, device=dev)
+        for j, it in enumerate(items):
+            self.mask_count(it['depth'], it['conf'], min_conf, mode, counts_d[j:j + 1])
+        counts_h = counts_d.cpu().tolist()                    # the one host synchronisation
+        local_counts = {it['pos']: int(c) for it, c in zip(items, counts_h)}
+        all_counts = bdist.exchange_counts(n_positions, local_counts, dev)
+        offs = np.concatenate([[0], np.cumsum(all_counts)]).astype(np.int64)
+        total = int(offs[-1])
+        dest = bdist.peer_cloud(dev, total)
+        if dest is not None:
+            buf_p, buf_c = dest
+            base = {it['pos']: int(offs[it['pos']]) for it in items}
+        elif rank == 0:
+            buf_p = torch.empty((total, 3), dtype=torch.float64, device=dev)
+            buf_c = torch.empty((total, 3), dtype=torch.uint8, device=dev)
+            base = {it['pos']: int(offs[it['pos']]) for it in items}
+        else:
+            mine_n = int(sum(local_counts.values()))
+            buf_p = torch.empty((mine_n, 3), dtype=torch.float64, device=dev)
+            buf_c = torch.empty((mine_n, 3), dtype=torch.uint8, device=dev)
+            run, base = 0, {}
+            for it in items:
+                base[it['pos']] = run
+                run += local_counts[it['pos']]
+        local = {}
+        dummy = torch.zeros(1, dtype=torch.int64, device=dev)
+        for it in items:
+            m, b = local_counts[it['pos']], base[it['pos']]
+            if m == 0:
+                continue
+            sl = (buf_p[b:b + m], buf_c[b:b + m])
+            self.mask_backproject(it['depth'], it['conf'], it['bgr'](), Kinv64, it['R'], it['t'], min_conf, mode,
+                                  points=sl[0], colors=sl[1], count=dummy, sync=False)
+            local[it['pos']] = sl
+        if dest is not None:
+            bdist.peer_fence(dev)                             # the back-projection kernels WERE the transfer
+            how = 'peer stores into rank 0 (symmetric memory over NVLink)'
+        else:
+            bdist.gather_into(all_counts, local, buf_p if rank == 0 else None, buf_c if rank == 0 else None)
+            how = 'NCCL point-to-point into the final slices' if ws > 1 else 'single rank'
+        if rank != 0:
+            return None, None, all_counts, how
+        return buf_p, buf_c, all_counts, how
+
     def mask_backproject(self, depth: torch.Tensor, conf: torch.Tensor, bgr: torch.Tensor, Kinv64: np.ndarray,
                          R: np.ndarray, t: np.ndarray, min_conf: float, mode: int,
                          points: Optional[torch.Tensor] = None, colors: Optional[torch.Tensor] = None,

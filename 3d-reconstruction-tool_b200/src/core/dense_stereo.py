@@ -147,18 +147,16 @@ class DenseStereoReconstructor:
                 st = torch.cuda.current_stream(eng.device)
                 for i in [ref_idx] + list(neighbors):
                     st.wait_event(ready[i])
-                out = self._sweep_device(ref_idx, neighbors, processed, poses, depth_min, depth_max, slot=slot)
-                bgr = self._color_on_device(processed, ref_idx)
-                return eng.mask_backproject(out['depth_map'], out['confidence'], bgr, Kinv, poses[ref_idx].R,
-                                            poses[ref_idx].t, float(self.min_views - 0.5), 1, sync=False, slot=slot)
+                return self._sweep_device(ref_idx, neighbors, processed, poses, depth_min, depth_max, slot=slot)
             jobs.append(job)
         results = eng.run_views(jobs, self.views_in_flight)
-        counts = torch.cat([cnt for _, _, cnt in results]).cpu().tolist() if results else []   # one synchronisation
-        local = {}
-        for (pos, ref_idx, _), (pts, cols, _), m in zip(plan, results, counts):
-            local[ref_idx] = (pts[:m], cols[:m])
-            print(f"  [{pos+1}/{len(ref_indices)}] Cam {ref_idx}: {m:,} pts")
-        pts_d, col_d = bdist.gather_point_clouds(ref_indices, local, eng.device)
+        # fusion with one host synchronisation: masks counted on the device, every view back-projected straight into its
+        # slice of rank 0's cloud (peer memory over NVLink when sharded; engine.fuse_to_rank0)
+        items = [dict(pos=pos, depth=out['depth_map'], conf=out['confidence'], R=poses[r].R, t=poses[r].t,
+                      bgr=(lambda r=r: self._color_on_device(processed, r))) for (pos, r, _), out in zip(plan, results)]
+        pts_d, col_d, all_counts, _ = eng.fuse_to_rank0(len(ref_indices), items, Kinv, float(self.min_views - 0.5), 1)
+        for pos, ref_idx, _ in plan:
+            print(f"  [{pos+1}/{len(ref_indices)}] Cam {ref_idx}: {int(all_counts[pos]):,} pts")
         if rank != 0:
             return np.array([]), np.array([])
         if self.device_postfilter and pts_d.shape[0]:

@@ -242,56 +242,17 @@ class PatchMatchMVS:
         if self.consistency == 'geometric':
             self._geometric_filter(plan, cam_indices, proc_images, poses, maps)
 
-        # ---- fusion: count every mask on the device, read the counts once, back-project into place
-        counts_d = torch.zeros(max(1, len(plan)), dtype=torch.int64, device=dev)
-        for j, (_, ref_idx, _) in enumerate(plan):
-            out = maps[ref_idx]
-            eng.mask_count(out['depth'], out['confidence'], float(self.min_views), 0, counts_d[j:j + 1])
-        counts_h = counts_d.cpu().tolist()                      # the one host synchronisation of the depth + fusion stage
-        tm['depth_maps_s'] = time.time() - t0
-        local_counts = {pos: int(c) for (pos, _, _), c in zip(plan, counts_h)}
-        for (pos, ref_idx, _), c in zip(plan, counts_h):
-            print(f"  [{pos+1}/{n_cams}] Cam {ref_idx}: {int(c):,} valid pixels")
-
-        print("\nFusing depth maps...")
+        # ---- fusion: count every mask on the device, read the counts once, back-project into place (engine.fuse_to_rank0)
+        items = [dict(pos=pos, depth=maps[r]['depth'], conf=maps[r]['confidence'], R=poses[r].R, t=poses[r].t,
+                      bgr=(lambda r=r: self._color_on_device(proc_images, r))) for pos, r, _ in plan]
+        torch.cuda.current_stream(dev).synchronize()           # phase boundary for the timing breakdown
         t1 = time.time()
-        all_counts = bdist.exchange_counts(n_cams, local_counts, dev)
-        offs = np.concatenate([[0], np.cumsum(all_counts)]).astype(np.int64)
-        total = int(offs[-1])
-        dest = bdist.peer_cloud(dev, total)                      # rank 0's cloud, peer-mapped over NVLink (or None)
-        if dest is not None:
-            buf_p, buf_c = dest                                 # every rank writes at the views' GLOBAL offsets
-            base = {pos: int(offs[pos]) for pos, _, _ in plan}
-        elif rank == 0:
-            buf_p = torch.empty((total, 3), dtype=torch.float64, device=dev)
-            buf_c = torch.empty((total, 3), dtype=torch.uint8, device=dev)
-            base = {pos: int(offs[pos]) for pos, _, _ in plan}
-        else:
-            mine_n = int(sum(local_counts.values()))
-            buf_p = torch.empty((mine_n, 3), dtype=torch.float64, device=dev)
-            buf_c = torch.empty((mine_n, 3), dtype=torch.uint8, device=dev)
-            run, base = 0, {}
-            for pos, _, _ in plan:
-                base[pos] = run
-                run += local_counts[pos]
-        local = {}
-        dummy = torch.zeros(1, dtype=torch.int64, device=dev)
+        tm['depth_maps_s'] = t1 - t0
+        buf_p, buf_c, all_counts, how = eng.fuse_to_rank0(n_cams, items, Kinv, float(self.min_views), 0)
         for pos, ref_idx, _ in plan:
-            m, b = local_counts[pos], base[pos]
-            if m == 0:
-                continue
-            out = maps[ref_idx]
-            sl = (buf_p[b:b + m], buf_c[b:b + m])
-            eng.mask_backproject(out['depth'], out['confidence'], self._color_on_device(proc_images, ref_idx), Kinv,
-                                 poses[ref_idx].R, poses[ref_idx].t, float(self.min_views), 0, points=sl[0],
-                                 colors=sl[1], count=dummy, sync=False)
-            local[pos] = sl
-        if dest is not None:
-            bdist.peer_fence(dev)                               # the back-projection kernels WERE the transfer
-            tm['gather'] = 'peer stores into rank 0 (symmetric memory over NVLink)'
-        else:
-            bdist.gather_into(all_counts, local, buf_p if rank == 0 else None, buf_c if rank == 0 else None)
-            tm['gather'] = 'NCCL point-to-point into the final slices' if ws > 1 else 'single rank'
+            print(f"  [{pos+1}/{n_cams}] Cam {ref_idx}: {int(all_counts[pos]):,} valid pixels")
+        print("\nFusing depth maps...")
+        tm['gather'] = how
         tm['fusion_gather_s'] = time.time() - t1
         if rank != 0:
             torch.cuda.current_stream(dev).synchronize()

@@ -39,17 +39,25 @@ def _run(rank, ws, port, q, mode='photometric'):
                        geo_min_views=1, geo_rel_thresh=0.02, geo_px_thresh=2.0,
                        schedule='viewprop' if mode == 'viewprop' else 'reference')
     sparse = np.stack([np.zeros(20), np.zeros(20), np.linspace(4.0, 6.0, 20)], axis=1)
-    p, c = pm.reconstruct(sc.images, poses, sparse_points=sparse)
+    if mode == 'stereo':
+        from core.dense_stereo import DenseStereoReconstructor
+        ds = DenseStereoReconstructor(cam, scale=1.0, num_depths=24, patch_size=5, device=f'cuda:{rank}')
+        p, c = ds.reconstruct(sc.images, poses)
+        p, c = np.asarray(p).reshape(-1, 3), np.asarray(c).reshape(-1, 3)
+    else:
+        p, c = pm.reconstruct(sc.images, poses, sparse_points=sparse)
     q.put((rank, p, c))
     if ws > 1:
         dist.destroy_process_group()
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize('mode', ['photometric', 'geometric', 'viewprop'])
+@pytest.mark.parametrize('mode', ['photometric', 'geometric', 'viewprop', 'stereo'])
 def test_two_rank_reconstruct_equals_single_rank(mode):
     """'geometric' additionally exercises the NCCL all-gather of the depth maps, 'viewprop' the per-iteration all-gather of
-    depth AND normal maps (the proposals are evaluated from snapshots, so the result must not depend on the sharding)."""
+    depth AND normal maps (the proposals are evaluated from snapshots, so the result must not depend on the sharding),
+    'stereo' the plane-sweep class.  With NVLink peer access the clouds travel as peer stores of the back-projection
+    kernels (dist.peer_cloud), otherwise over NCCL point-to-point; the result must be the single-rank cloud either way."""
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     ctx = mp.get_context('spawn')
