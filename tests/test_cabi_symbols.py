@@ -59,3 +59,21 @@ def test_engine_refuses_to_run_without_cuda():
     from b200dense.engine import DenseEngine
     with pytest.raises(_cabi.B200DenseError):
         DenseEngine('cuda:0')
+
+
+def test_integration_md_structs_match_the_binding():
+    """The ctypes structures INTEGRATION.md tells a reference maintainer to write are the ones the tested binding uses
+    (same field names, order and C types), and every entry point its table names is exported."""
+    text = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    ns = {}
+    block = re.search(r'class Cams\(C\.Structure\):.*?lib\.b200d_last_error\.restype', text, flags=re.S).group(0)
+    block = block.rsplit('\n', 2)[0]
+    exec('import ctypes as C\n' + block, ns)                      # noqa: S102  (our own documentation snippet)
+    for name in ('Cams', 'PmParams', 'Rng'):
+        doc, real = ns[name], getattr(_cabi, name)
+        assert [(f[0], f[1]) for f in doc._fields_] == [(f[0], f[1]) for f in real._fields_], name
+        assert C.sizeof(doc) == C.sizeof(real)
+    lib = _cabi.load()
+    types = {'b200d_status', 'b200d_cams', 'b200d_pm_params', 'b200d_rng', 'b200d_arith'}
+    for sym in set(re.findall(r'`(b200d_[a-z0-9_]+)', text)) - types:
+        assert hasattr(lib, sym), sym
