@@ -329,11 +329,18 @@ __device__ unsigned long long g_sweep_fallbacks;
 // ------------------------------------------------------------------------------------------------ NCC kernel
 // Same tile, TMA pipeline and epilogue rules as ncc_kernel.  MODE: N_COST, N_CONF, N_SHIFT, N_REFINE, N_VPROP, N_SWEEP
 // for A_FAST; N_SWEEP only for A_HYBRID.
-#ifndef B200D_SEP_MIN_BLOCKS
-#define B200D_SEP_MIN_BLOCKS 3
+// Resident CTAs per SM.  Plane sweep: 3 (its sampling kernel is coalesced, the NCC kernel wants the warps).  PatchMatch
+// modes of B200D_FAST: 2 -- measured on B200 (profiles/microbench/r02_variants_cmd.sh): three 70 KB CTAs take 212 KB of the
+// SM's 256 KB L1 / shared memory and starve the gather-bound sampling kernels of the other views in flight; with two, the
+// isolated NCC launch is slower (90 -> 103 us) but the step is 22 % faster (209 -> 255 views/s).
+#ifndef B200D_SEP_MIN_BLOCKS_SWEEP
+#define B200D_SEP_MIN_BLOCKS_SWEEP 3
+#endif
+#ifndef B200D_SEP_MIN_BLOCKS_PM
+#define B200D_SEP_MIN_BLOCKS_PM 2
 #endif
 template <int K, int MODE, int ARITH>
-__global__ void __launch_bounds__(NT, B200D_SEP_MIN_BLOCKS) ncc_sep_kernel(const __grid_constant__ NccArgs a) {
+__global__ void __launch_bounds__(NT, (MODE == N_SWEEP) ? B200D_SEP_MIN_BLOCKS_SWEEP : B200D_SEP_MIN_BLOCKS_PM) ncc_sep_kernel(const __grid_constant__ NccArgs a) {
     using G = Geo<K>;
     using FG = FGeo<K>;
     constexpr int HALF = G::HALF;
