@@ -520,6 +520,7 @@ __global__ void __launch_bounds__(NT, (MODE == N_SWEEP) ? B200D_SEP_MIN_BLOCKS_S
     }
 
     // ---- epilogue (same rules as ncc_kernel)
+    unsigned wins = 0;                                     // N_REFINE: bit q*PX+p = output (q,p) of this thread won
 #pragma unroll
     for (int q = 0; q < QY; ++q)
 #pragma unroll
@@ -560,31 +561,25 @@ __global__ void __launch_bounds__(NT, (MODE == N_SWEEP) ? B200D_SEP_MIN_BLOCKS_S
                 }
                 continue;
             }
+            if (MODE == N_REFINE) {
+                // winners' normals: perturbed below, compacted over the warp (refine_normals_compacted); a loser only
+                // carries its normal over when the evaluation is not in place
+                wins |= better ? 1u << (q * PX + p) : 0u;
+                if (!better && a.normal_out != a.normal_in) {
+                    const float *np = a.normal_in + 3 * g;
+                    float *no = a.normal_out + 3 * g;
+                    no[0] = np[0]; no[1] = np[1]; no[2] = np[2];
+                }
+                continue;
+            }
             float n0, n1, n2;
             if (better) {
-                if (MODE == N_SHIFT) {
-                    const int nx = gx + a.dx, ny = gy + a.dy;
-                    if (nx >= 0 && nx < W && ny >= 0 && ny < H) {
-                        const float *np = a.normal_in + 3 * ((size_t)ny * W + nx);
-                        n0 = np[0]; n1 = np[1]; n2 = np[2];
-                    } else {
-                        n0 = n1 = n2 = 0.0f;
-                    }
+                const int nx = gx + a.dx, ny = gy + a.dy;                       // N_SHIFT: the neighbour's normal
+                if (nx >= 0 && nx < W && ny >= 0 && ny < H) {
+                    const float *np = a.normal_in + 3 * ((size_t)ny * W + nx);
+                    n0 = np[0]; n1 = np[1]; n2 = np[2];
                 } else {
-                    float r0, r1, r2;
-                    if (a.rand_n) {
-                        const float *rp = a.rand_n + 3 * g;
-                        r0 = __ldg(rp); r1 = __ldg(rp + 1); r2 = __ldg(rp + 2);
-                    } else {
-                        const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-                        const uint4 ra = philox4x32_10(make_uint4((uint32_t)g, a.eval_id, a.view_id, 1u), key);
-                        gauss2(ra.x, ra.y, r0, r1);
-                        r2 = gauss(ra.z, ra.w);
-                    }
-                    const float *np = a.normal_in + 3 * g;
-                    const float c0 = fmaf(r0, a.nr, np[0]), c1 = fmaf(r1, a.nr, np[1]), c2 = fmaf(r2, a.nr, np[2]);
-                    const float in_ = rsqrtf(fmaxf(fmaf(c0, c0, fmaf(c1, c1, c2 * c2)), 1e-24f));
-                    n0 = c0 * in_; n1 = c1 * in_; n2 = c2 * in_;
+                    n0 = n1 = n2 = 0.0f;
                 }
             } else if (a.normal_out != a.normal_in) {
                 const float *np = a.normal_in + 3 * g;
@@ -595,6 +590,7 @@ __global__ void __launch_bounds__(NT, (MODE == N_SWEEP) ? B200D_SEP_MIN_BLOCKS_S
                 no[0] = n0; no[1] = n1; no[2] = n2;
             }
         }
+    if (MODE == N_REFINE) refine_normals_compacted(a, wins, x0, y0, tid, W);
 }
 
 }  // namespace b200d

@@ -195,6 +195,57 @@ __device__ __forceinline__ void box_sums(const float *__restrict__ s_s, const fl
     box_row<K, false, true>(s_s + base + K * RWP, s_r + base + K * RWP, as, ass, ars);
 }
 
+// ---- N_REFINE: normal_new = F.normalize(normal + randn * normal_range) for the winners (mvs_patchmatch.py:475-476, :486-489).
+// In the later evaluations a few per cent of the pixels win, yet nearly every (warp, output slot) has a winner in
+// some lane, so running this per output slot would cost the full Philox + Box-Muller + normalise sequence eight
+// times per warp.  Instead the warp enumerates its winners (ballot per slot, prefix of the counts) and lane l
+// takes winners l, l+32, ...: each winner is processed once, by whichever lane, straight from / to global memory.
+// `wins`: bit q*PX+p = output (q,p) of this thread won.  Called by every lane of the warp (exact and separable kernels).
+__device__ __forceinline__ void refine_normals_compacted(const NccArgs &a, unsigned wins, int x0, int y0, int tid, int W) {
+    const int lane = tid & 31;
+    __syncwarp();
+    unsigned m_sel = 0, b_sel = 0, total_w = 0;        // mask / first winner index of the slot this lane's winner is in
+    // lane-uniform tables would need dynamic indexing; instead each lane keeps what it needs for w = lane + 32*it
+    unsigned masks[QY * PX], bases[QY * PX + 1];
+    bases[0] = 0;
+#pragma unroll
+    for (int sl = 0; sl < QY * PX; ++sl) {
+        masks[sl] = __ballot_sync(0xffffffffu, (wins >> sl) & 1u);
+        bases[sl + 1] = bases[sl] + __popc(masks[sl]);
+    }
+    total_w = bases[QY * PX];
+    const int warp_tid0 = tid & ~31;
+    for (unsigned w = lane; w < total_w; w += 32) {
+        int sl = 0;
+        m_sel = masks[0];
+        b_sel = 0;
+#pragma unroll
+        for (int k = 1; k < QY * PX; ++k)
+            if (w >= bases[k]) { sl = k; m_sel = masks[k]; b_sel = bases[k]; }
+        const int owner = warp_tid0 + (int)__fns(m_sel, 0, (int)(w - b_sel) + 1);
+        const int gx = x0 + (owner % NTX) * PX + sl % PX, gy = y0 + (owner / NTX) * QY + sl / PX;
+        const size_t g = (size_t)gy * W + gx;
+        float r0, r1, r2;
+        if (a.rand_n) {
+            const float *rp = a.rand_n + 3 * g;
+            r0 = __ldg(rp); r1 = __ldg(rp + 1); r2 = __ldg(rp + 2);
+        } else {
+            const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+            const uint4 ra = philox4x32_10(make_uint4((uint32_t)g, a.eval_id, a.view_id, 1u), key);
+            gauss2(ra.x, ra.y, r0, r1);
+            r2 = gauss(ra.z, ra.w);
+        }
+        const float *np = a.normal_in + 3 * g;
+        const float c0 = add(np[0], mul(r0, a.nr));
+        const float c1 = add(np[1], mul(r1, a.nr));
+        const float c2 = add(np[2], mul(r2, a.nr));
+        float nn = __fsqrt_rn(add(add(mul(c0, c0), mul(c1, c1)), mul(c2, c2)));
+        nn = nn < 1e-12f ? 1e-12f : nn;
+        float *no = a.normal_out + 3 * g;
+        no[0] = div_(c0, nn); no[1] = div_(c1, nn); no[2] = div_(c2, nn);
+    }
+}
+
 // Plane sweep: `ncc > thresh` for ncc = cov / sqrt(x), x = var1*var2 + 1e-8 (dense_stereo.py:303, 344-345), decided
 // without the square root and the division whenever cov^2 is clearly off thresh^2 * x (t_lo = ((1 - 1e-5) thresh)^2,
 // t_hi = ((1 + 1e-5) thresh)^2: the computed quotient is within (1 +- 4u) of cov / sqrt(x) and the squared comparison
@@ -468,54 +519,7 @@ __global__ void __launch_bounds__(NT, B200D_MIN_BLOCKS) ncc_kernel(const __grid_
             }
         }
 
-    // ---- N_REFINE: normal_new = F.normalize(normal + randn * normal_range) for the winners (:475-476, :486-489).
-    // In the later evaluations a few per cent of the pixels win, yet nearly every (warp, output slot) has a winner in
-    // some lane, so running this per output slot would cost the full Philox + Box-Muller + normalise sequence eight
-    // times per warp.  Instead the warp enumerates its winners (ballot per slot, prefix of the counts) and lane l
-    // takes winners l, l+32, ...: each winner is processed once, by whichever lane, straight from / to global memory.
-    if (MODE == N_REFINE) {
-        __syncwarp();
-        unsigned m_sel = 0, b_sel = 0, total_w = 0;        // mask / first winner index of the slot this lane's winner is in
-        // lane-uniform tables would need dynamic indexing; instead each lane keeps what it needs for w = lane + 32*it
-        unsigned masks[QY * PX], bases[QY * PX + 1];
-        bases[0] = 0;
-#pragma unroll
-        for (int sl = 0; sl < QY * PX; ++sl) {
-            masks[sl] = __ballot_sync(0xffffffffu, (wins >> sl) & 1u);
-            bases[sl + 1] = bases[sl] + __popc(masks[sl]);
-        }
-        total_w = bases[QY * PX];
-        const int warp_tid0 = tid & ~31;
-        for (unsigned w = lane; w < total_w; w += 32) {
-            int sl = 0;
-            m_sel = masks[0];
-            b_sel = 0;
-#pragma unroll
-            for (int k = 1; k < QY * PX; ++k)
-                if (w >= bases[k]) { sl = k; m_sel = masks[k]; b_sel = bases[k]; }
-            const int owner = warp_tid0 + (int)__fns(m_sel, 0, (int)(w - b_sel) + 1);
-            const int gx = x0 + (owner % NTX) * PX + sl % PX, gy = y0 + (owner / NTX) * QY + sl / PX;
-            const size_t g = (size_t)gy * W + gx;
-            float r0, r1, r2;
-            if (a.rand_n) {
-                const float *rp = a.rand_n + 3 * g;
-                r0 = __ldg(rp); r1 = __ldg(rp + 1); r2 = __ldg(rp + 2);
-            } else {
-                const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-                const uint4 ra = philox4x32_10(make_uint4((uint32_t)g, a.eval_id, a.view_id, 1u), key);
-                gauss2(ra.x, ra.y, r0, r1);
-                r2 = gauss(ra.z, ra.w);
-            }
-            const float *np = a.normal_in + 3 * g;
-            const float c0 = add(np[0], mul(r0, a.nr));
-            const float c1 = add(np[1], mul(r1, a.nr));
-            const float c2 = add(np[2], mul(r2, a.nr));
-            float nn = __fsqrt_rn(add(add(mul(c0, c0), mul(c1, c1)), mul(c2, c2)));
-            nn = nn < 1e-12f ? 1e-12f : nn;
-            float *no = a.normal_out + 3 * g;
-            no[0] = div_(c0, nn); no[1] = div_(c1, nn); no[2] = div_(c2, nn);
-        }
-    }
+    if (MODE == N_REFINE) refine_normals_compacted(a, wins, x0, y0, tid, W);
 }
 
 }  // namespace b200d
