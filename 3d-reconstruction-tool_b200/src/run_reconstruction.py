@@ -11,6 +11,9 @@ from one of:
     sparse run or a synthetic scene;
   * the reference's own `SfMPipeline`, if its `src` directory is given in $REF_SRC (it is imported
     and run unmodified; nothing of it is vendored here).
+Multi-GPU: `torchrun --nproc-per-node N -m src.run_reconstruction ...` shards the reference views over N GPUs (rank 0
+writes the files).  Extra flags `--arith`, `--schedule`, `--consistency` select this engine's opt-in modes (defaults =
+the reference's behaviour).
 Precedence mvs > stereo, skipped with --fast or fewer than 3 poses; outputs `dense_mvs.ply` /
 `dense_stereo.ply` -- all as in the reference (:118-172).  `--dense` (CPU SIFT matching,
 reference src/core/dense.py) is not part of the GPU path and is rejected.
@@ -46,7 +49,29 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument('--poses', type=str, default=None, help='Known poses (.npz) instead of running sparse SfM')
     p.add_argument('--calibration', type=str, default=None, help='calibration_data.npz (keys mtx, dist)')
     p.add_argument('--scale', type=float, default=0.25, help='Working resolution scale (reference: 0.25)')
+    # not in the reference (defaults = the reference's behaviour): opt-in modes of this engine
+    p.add_argument('--arith', choices=['parity', 'fast'], default='parity',
+                   help="'parity' = bit-exact with the reference (default); 'fast' = re-associated arithmetic, NOT bit-exact")
+    p.add_argument('--schedule', choices=['reference', 'redblack', 'viewprop'], default='reference',
+                   help='PatchMatch propagation schedule; redblack / viewprop are extensions without a reference counterpart')
+    p.add_argument('--consistency', choices=['photometric', 'geometric'], default='photometric',
+                   help="'geometric' adds the cross-view depth-map check (extension)")
     return p
+
+
+def init_distributed():
+    """Under `torchrun --nproc-per-node N` the dense stage shards the reference views over N GPUs (one process per GPU,
+    NCCL); rank 0 returns / writes the cloud.  Without torchrun this is a no-op (single GPU)."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world <= 1:
+        return 0, 1
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    return dist.get_rank(), world
 
 
 def load_known_poses(path: Path, image_dir: Path, max_images=None):
@@ -88,6 +113,8 @@ def run_reference_sfm(calibration_path, image_dir, args):
 
 def main(argv=None):
     args = build_parser().parse_args(argv)
+    rank, world = init_distributed()
+    device = f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}" if world > 1 else None
     project_root = src_dir.parent
     calibration_path = Path(args.calibration) if args.calibration else (
         project_root / 'src' / 'calibration' / 'calibration_results' / 'calibration_data.npz')
@@ -122,8 +149,9 @@ def main(argv=None):
         images, pose_dict, points, colors = load_known_poses(Path(args.poses), image_dir, args.max_images)
     else:
         images, pose_dict, points, colors = run_reference_sfm(calibration_path, image_dir, args)
-    save_ply(points, colors, str(output_dir / 'sparse.ply'))
-    save_cameras_ply(pose_dict, str(output_dir / 'cameras.ply'))
+    if rank == 0:
+        save_ply(points, colors, str(output_dir / 'sparse.ply'))
+        save_cameras_ply(pose_dict, str(output_dir / 'cameras.ply'))
 
     run_dense = (args.mvs or args.stereo) and not args.fast
     if run_dense and len(pose_dict) >= 3:
@@ -133,18 +161,19 @@ def main(argv=None):
             print("Starting PatchMatch MVS...")
             print("=" * 60)
             from core.mvs_patchmatch import PatchMatchMVS
-            mvs = PatchMatchMVS(camera, scale=args.scale, num_iterations=3, min_views=3)
+            mvs = PatchMatchMVS(camera, scale=args.scale, num_iterations=3, min_views=3, arith=args.arith,
+                                schedule=args.schedule, consistency=args.consistency, device=device)
             dense_points, dense_colors = mvs.reconstruct(images, pose_dict,
                                                          sparse_points=points if len(points) else None)
-            if len(dense_points) > 0:
+            if rank == 0 and len(dense_points) > 0:
                 dense_output = output_dir / 'dense_mvs.ply'
                 save_ply(dense_points, dense_colors, str(dense_output))
                 print(f"Saved {len(dense_points):,} points to {dense_output}")
         else:
             from core.dense_stereo import DenseStereoReconstructor
-            stereo = DenseStereoReconstructor(camera, scale=args.scale)
+            stereo = DenseStereoReconstructor(camera, scale=args.scale, arith=args.arith, device=device)
             dense_points, dense_colors = stereo.reconstruct(images, pose_dict, max_pairs=30)
-            if len(dense_points) > 0:
+            if rank == 0 and len(dense_points) > 0:
                 dense_output = output_dir / 'dense_stereo.ply'
                 save_ply(dense_points, dense_colors, str(dense_output))
                 print(f"Saved {len(dense_points):,} points to {dense_output}")
@@ -159,6 +188,10 @@ def main(argv=None):
     elif args.stereo:
         print("  - dense_stereo.ply: Plane sweep cloud")
     print(f"  - cameras.ply: {len(pose_dict)} camera positions")
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':
