@@ -131,8 +131,22 @@ def peer_cloud(device: torch.device, n_points: int) -> Optional[Tuple[torch.Tens
     pc = _PEER.setdefault(device, _PeerCloud(device))
     if n_points > pc.cap:                                   # same decision on every rank: n_points and cap history agree
         ok = 1
+        if pc.cap == 0:
+            # first use: only try symmetric memory where every rank's GPU can map rank 0's GPU directly (NVLink / PCIe
+            # peer access); the verdict is agreed on below, so a box without peer access takes the NCCL path everywhere
+            try:
+                visible = torch.cuda.device_count()
+                mine = device.index if device.index is not None else torch.cuda.current_device()
+                peers_ok = all(p == mine or torch.cuda.can_device_access_peer(mine, p) for p in range(min(ws, visible)))
+                ok = 1 if (visible >= ws and peers_ok) else 0
+            except Exception:                               # noqa: BLE001
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = int(flag.item())
         try:
-            pc.ensure(n_points)
+            if ok:
+                pc.ensure(n_points)
         except Exception:                                   # noqa: BLE001  (driver / fabric without peer mapping)
             ok = 0
         flag = torch.tensor([ok], dtype=torch.int32, device=device)
