@@ -11,9 +11,12 @@
 //   ARITH = A_HYBRID  plane sweep in PARITY mode.  The sweep only ever uses the NCC through `ncc > thresh`
 //                     (dense_stereo.py:303), so the comparison is first decided from the separable sums together
 //                     with a rigorous bound on their distance to the reference's chains (derivation at
-//                     sweep_decide_bounded); the few outputs the bound cannot decide (~2e-4) make their warp redo the
-//                     window with the exact row-major chains (box_sums) from the tile still in shared memory.  Counts
-//                     and arg-max stay bit-identical to the oracle; the sampling kernel is the parity one.
+//                     sweep_decide_bounded); the few outputs the bound cannot decide (0.08 % on the benchmark scene)
+//                     are remembered and redone one by one, after the neighbour loop, with the exact row-major chains
+//                     read from the L2-resident sampled maps (exact_one_global).  Counts and arg-max stay
+//                     bit-identical to the oracle; the sampling kernel is the parity one.
+//   ARITH = A_CHECK   diagnostic twin of A_HYBRID: also evaluates the chains for every output and records the largest
+//                     observed |separable - chain| / bound (never above 0.36: tests/test_gpu_sweep_hybrid.py).
 //
 // Window sums, per CTA tile (TW x TH outputs, window (TW+K-1) x (TH+K-1) in shared memory via TMA as before):
 //   H phase  every (window row, group of 4 output columns): products s*s, r*s, then the K-tap horizontal sums of
