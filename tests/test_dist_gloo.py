@@ -97,3 +97,8 @@ def test_single_process_paths():
     assert e.shape == (0, 3)
     maps = bdist.all_gather_maps([7, 9], {7: torch.ones(2, 2), 9: torch.zeros(2, 2)}, (2, 2), torch.device('cpu'))
     assert torch.equal(maps[7], torch.ones(2, 2)) and torch.equal(maps[9], torch.zeros(2, 2))
+    # single rank: counts are the local ones, the in-place gather is a no-op, and there is no peer buffer to map
+    assert bdist.exchange_counts(4, {0: 3, 2: 5}, torch.device('cpu')) == [3, 0, 5, 0]
+    bdist.gather_into([3, 0, 5, 0], {}, None, None)
+    assert bdist.peer_cloud(torch.device('cpu'), 100) is None
+    assert bdist.owner_of(5, 4) == 1
