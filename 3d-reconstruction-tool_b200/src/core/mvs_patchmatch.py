@@ -172,8 +172,9 @@ class PatchMatchMVS:
         `views_in_flight` at a time on separate streams of each GPU.  Rank 0 returns the fused and filtered
         cloud in the reference's order (sorted views, row-major pixels); other ranks return (0,3) arrays.
         The fusion stage synchronises with the host once (to size the cloud): every view's mask is counted on the
-        device, then each view is back-projected straight into its slice of the final buffer -- on rank 0 the other
-        ranks' slices arrive by NCCL point-to-point transfers into place."""
+        device, then each view is back-projected straight into its slice of the final buffer (DenseEngine.fuse_to_rank0)
+        -- in a multi-GPU job the other ranks' kernels store into rank 0's buffer through NVLink peer mappings (NCCL
+        point-to-point into the final slices where peer memory is unavailable)."""
         from b200dense import dist as bdist
         rank, ws = bdist.world()
         print("\n" + "=" * 60)
