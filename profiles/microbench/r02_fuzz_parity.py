@@ -1,7 +1,8 @@
 """Randomised parity stress (GPU box): for `seconds` of wall time draw random sizes / window sizes / neighbour counts /
 thresholds / image transforms and check
   * plane sweep: B200D_PARITY (bounded decision) == B200D_PARITY_CHAINS == oracle (counts, arg-max, depth),
-  * PatchMatch cost + confidence of a random depth map == oracle (bit-exact, NaN-aware),
+  * PatchMatch cost + confidence of a random depth map == oracle (bit-exact, NaN-aware); at small sizes a full
+    PatchMatch view with injected random numbers == oracle (depth, normal, confidence, best cost),
   * geometric-consistency and view-propagation proposal kernels == their definitions in oracle/dense_oracle.c.
 Prints one summary line; exits non-zero on the first mismatch.   python profiles/microbench/r02_fuzz_parity.py [seconds]"""
 import os
@@ -23,7 +24,7 @@ seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
 eng = DenseEngine('cuda:0')
 rng = np.random.default_rng(int(os.environ.get('FUZZ_SEED', '0')))
 t_end = time.time() + seconds
-n_cases = {'sweep': 0, 'pm': 0, 'geo': 0, 'vprop': 0}
+n_cases = {'sweep': 0, 'pm': 0, 'pm_view': 0, 'geo': 0, 'vprop': 0}
 
 
 def transform(g, how):
@@ -44,6 +45,8 @@ def transform(g, how):
 
 while time.time() < t_end:
     W, H = int(rng.integers(40, 420)), int(rng.integers(36, 300))
+    if rng.random() < 0.4:
+        W, H = int(rng.integers(40, 160)), int(rng.integers(36, 120))      # small cases also run a full PatchMatch view
     n = int(rng.integers(3, 10))
     kind = str(rng.choice(['wavy', 'plane', 'turntable']))
     sc = make_scene(kind, n, W, H, seed=int(rng.integers(0, 1 << 30)), arc_deg=float(rng.uniform(2.0, 9.0)))
@@ -85,6 +88,21 @@ while time.time() < t_end:
             print(f'MISMATCH pm_cost mode {mode}: {kind} {W}x{H} k={k} S={len(nb)} {how}: {int((got != exp).sum())}')
             sys.exit(1)
     n_cases['pm'] += 1
+    # ---- a full PatchMatch view with injected random numbers (small sizes: the oracle runs every evaluation on the CPU)
+    if W * H <= 160 * 120 and len(nb) >= 2:
+        iters, samples = int(rng.integers(1, 3)), int(rng.integers(1, 4))
+        n0 = rng.standard_normal((H, W, 3)).astype(F)
+        n0 /= np.linalg.norm(n0, axis=-1, keepdims=True)
+        ru = rng.random((iters * samples, H, W), dtype=F)
+        rn = rng.standard_normal((iters * samples, H, W, 3)).astype(F)
+        out = eng.pm_view(dref, dnb, ecams, k, iters, samples, dmin, dmax, init_depth=d(depth), init_normal=d(n0),
+                          rand_u=d(ru), rand_n=d(rn), want_best=True)
+        exp = orc.pm_view(gray[ref], [gray[i] for i in nb], ocams, k, iters, samples, dmin, dmax, depth, n0, ru, rn)
+        for key in ('depth', 'normal', 'confidence', 'best_cost'):
+            if not np.array_equal(out[key].cpu().numpy(), exp[key], equal_nan=True):
+                print(f'MISMATCH pm_view {key}: {kind} {W}x{H} k={k} S={len(nb)} it={iters} sm={samples} {how}')
+                sys.exit(1)
+        n_cases['pm_view'] += 1
     # ---- cross-view extension kernels vs their definitions
     maps = [(sc.depth_gt[i] * (1 + 0.01 * rng.standard_normal(sc.depth_gt[i].shape))).astype(F) for i in range(n)]
     px, rel = float(rng.choice([0.5, 1.0, 2.5])), float(rng.choice([0.003, 0.01, 0.05]))
