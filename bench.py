@@ -233,6 +233,20 @@ def run_reference(a):
         'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
 
+def guarded(world, name, fn):
+    """Secondary legs must not cost the headline line: on a single GPU a failing leg is reported as {'error': ...}.  With
+    several ranks an exception has to propagate (a rank that skipped a leg would leave the others waiting in its
+    collectives; the launcher then ends the whole job)."""
+    if world > 1:
+        return fn()
+    try:
+        return fn()
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        traceback.print_exc(file=sys.stderr)
+        return {'error': f'{name} leg failed: {type(e).__name__}: {e}'}
+
+
 def load_json(path):
     try:
         return json.load(open(path))
@@ -616,12 +630,13 @@ def main():
     # ---- end to end through reconstruct(): host photographs -> depth maps -> fusion -> gather -> post-filter -> host cloud
     e2e_rec = None
     if not a.no_extras and not a.no_e2e:
-        e2e_rec = reconstruct_leg(a, dev, world, barrier, max_over_ranks)
+        e2e_rec = guarded(world, 'e2e_reconstruct', lambda: reconstruct_leg(a, dev, world, barrier, max_over_ranks))
 
     # ---- secondary metric: plane sweep Gpix*planes/s (BASELINE configs[2] shape)
     sweep = None
     if not a.no_plane_sweep:
-        sweep = sweep_leg(a, eng, dev, rank, world, barrier, max_over_ranks, fp32_peak)
+        sweep = guarded(world, 'plane_sweep',
+                        lambda: sweep_leg(a, eng, dev, rank, world, barrier, max_over_ranks, fp32_peak))
 
     # ---- the opt-in fast arithmetic beside the parity line (never the default; agreement measured by the tests)
     fast_mode = None
