@@ -354,6 +354,7 @@ void fill_sample(SampleArgs &s, const float *const *d_src, const b200d_cams *cam
     memset(&s, 0, sizeof(s));
     for (int i = 0; i < cams->n_src; ++i) s.src[i] = d_src[i];
     s.cams = *cams;
+    fill_pair_cams(s.pc, s.cams);
     s.H = H; s.W = W; s.Wp = sc.Wp; s.map_stride = sc.map_stride;
     s.half = patch / 2;
     s.pad = (patch / 2) % 4;

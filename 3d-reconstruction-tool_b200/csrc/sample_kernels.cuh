@@ -25,6 +25,7 @@ enum BoundsMode { B_PATCH = 0, B_IMAGE = 1, B_DEPTH = 2 };   // validity test of
 struct SampleArgs {
     const float *src[B200D_MAX_SRC];
     b200d_cams cams;
+    SrcPairCams pc[B200D_MAX_SRC / 2];   // R_src / t_src of sources (2i, 2i+1) interleaved (fill_pair_cams)
     int H, W, Wp, pad;                   // sampled maps: row pitch Wp floats, pixel x at column x + pad
     size_t map_stride;                   // floats between consecutive sampled maps
     const float *depth_in;               // (H,W) current depth (C_MAP / C_SHIFT / C_REFINE)
@@ -42,11 +43,27 @@ struct SampleArgs {
 
 constexpr int SBX = 32, SBY = 8;         // thread block: 32 x 8 pixels
 
+// Sources are processed two at a time through the packed fp32x2 path (project_sample_fast2); an odd count leaves one
+// source to the scalar path.  B200D_SAMPLE_PAIRS=0 builds the all-scalar twin (A/B measurements; identical results).
+#ifndef B200D_SAMPLE_PAIRS
+#define B200D_SAMPLE_PAIRS 1
+#endif
+#ifndef B200D_SAMPLE_MIN_BLOCKS
+#define B200D_SAMPLE_MIN_BLOCKS 6
+#endif
+
+inline void fill_pair_cams(SrcPairCams *pc, const b200d_cams &c) {
+    for (int i = 0; i < B200D_MAX_SRC / 2; ++i) {
+        for (int j = 0; j < 9; ++j) pc[i].R[j] = make_float2(c.R_src[2 * i][j], c.R_src[2 * i + 1][j]);
+        for (int j = 0; j < 3; ++j) pc[i].t[j] = make_float2(c.t_src[2 * i][j], c.t_src[2 * i + 1][j]);
+    }
+}
+
 // NS > 0: number of sources known at compile time -- the loop is fully unrolled and every camera constant becomes a
 // constant-bank operand of the arithmetic instruction that uses it (no uniform loads, no index arithmetic);
 // NS == 0: run-time count.
 template <int CAND, int BOUNDS, int NS>
-__global__ void __launch_bounds__(SBX *SBY, 6) sample_kernel(const __grid_constant__ SampleArgs a) {
+__global__ void __launch_bounds__(SBX *SBY, B200D_SAMPLE_MIN_BLOCKS) sample_kernel(const __grid_constant__ SampleArgs a) {
     const int x = blockIdx.x * SBX + threadIdx.x, y = blockIdx.y * SBY + threadIdx.y;
     if (x >= a.W || y >= a.H) return;
     const int W = a.W, H = a.H;
@@ -99,13 +116,38 @@ __global__ void __launch_bounds__(SBX *SBY, 6) sample_kernel(const __grid_consta
         vmask |= (unsigned)ok << s;
         out[(size_t)s * a.map_stride] = smp;
     };
+    auto two_sources = [&](int s) {          // sources s and s + 1 (s even)
+        float u[2], v[2], z[2], smp[2];
+        bool trusted[2];
+        project_sample_fast2(a.cams, a.pc[s >> 1], pw, a.src[s], a.src[s + 1], W, H, wm1, hm1, rw, rh, u, v, z, smp, trusted);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (!trusted[h]) {
+                float uv[2];
+                smp[h] = project_sample_exact(a.cams, s + h, pw, a.src[s + h], W, H, wm1, hm1, uv);
+                u[h] = uv[0];
+                v[h] = uv[1];
+            }
+            bool ok = z[h] > 0.1f;
+            if (BOUNDS != B_DEPTH) ok = ok & (u[h] >= lo) & (u[h] < hix) & (v[h] >= lo) & (v[h] < hiy);
+            vmask |= (unsigned)ok << (s + h);
+            out[(size_t)(s + h) * a.map_stride] = smp[h];
+        }
+    };
     if (NS > 0) {
 #pragma unroll
-        for (int s = 0; s < NS; ++s) one_source(s);
+        for (int s = 0; s + 1 < NS; s += 2) {
+            if (B200D_SAMPLE_PAIRS) two_sources(s);
+            else { one_source(s); one_source(s + 1); }
+        }
+        if (NS & 1) one_source(NS - 1);
     } else {
         const int S = a.cams.n_src;
+        int s = 0;
+        if (B200D_SAMPLE_PAIRS)
+            for (; s + 1 < S; s += 2) two_sources(s);
 #pragma unroll 2
-        for (int s = 0; s < S; ++s) one_source(s);
+        for (; s < S; ++s) one_source(s);
     }
     if (a.cand) a.cand[g] = cd;
     a.valid[g] = (uint8_t)vmask;
