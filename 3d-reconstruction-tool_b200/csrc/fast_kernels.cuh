@@ -213,6 +213,30 @@ __device__ __forceinline__ void vphase(const float *__restrict__ h, int tx, int 
     mul2_store(o[1][2], o[1][3], add2(c1, pack2(ak.z, ak.w)), w2);
 }
 
+// Same sums, results left packed: o[q][0] = outputs (q,0),(q,1), o[q][1] = outputs (q,2),(q,3) -- the bounded decision
+// below works on two outputs per instruction.
+template <int K>
+__device__ __forceinline__ void vphase2(const float *__restrict__ h, int tx, int ty, unsigned long long (&o)[QY][2]) {
+    static_assert(QY == 2 && PX == 4, "thread tile is 4 x 2");
+    constexpr float w = 1.0f / (float)(K * K);
+    constexpr int RS = TW / 4;
+    const float4 *p = reinterpret_cast<const float4 *>(h + (ty * QY) * TW + tx * PX);
+    float4 t = p[RS];
+    unsigned long long c0 = pack2(t.x, t.y), c1 = pack2(t.z, t.w);
+#pragma unroll
+    for (int i = 2; i < K; ++i) {
+        t = p[i * RS];
+        c0 = add2(c0, pack2(t.x, t.y));
+        c1 = add2(c1, pack2(t.z, t.w));
+    }
+    const float4 a0 = p[0], ak = p[K * RS];
+    const unsigned long long w2 = pack2(w, w);
+    o[0][0] = f2mul(add2(c0, pack2(a0.x, a0.y)), w2);
+    o[0][1] = f2mul(add2(c1, pack2(a0.z, a0.w)), w2);
+    o[1][0] = f2mul(add2(c0, pack2(ak.x, ak.y)), w2);
+    o[1][1] = f2mul(add2(c1, pack2(ak.z, ak.w)), w2);
+}
+
 // ------------------------------------------------------------------------------------------------ bounded decision
 // Decide `ncc > thresh` for the reference's NCC  ncc = cov / sqrt(var1*var2 + 1e-8)  (dense_stereo.py:337-345) from the
 // separable sums m2~, a2~ = box(s*s)~, ar~ = box(r*s)~, without knowing the reference's own (chain) values m2, a2, ar.
@@ -255,6 +279,15 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+// Flush-to-zero form: one MUFU instead of MUFU + four fix-up instructions for subnormal operands.  A subnormal x is
+// read as 0, so the result can fall short of sqrt(x) by at most sqrt(2^-126) < SQRT_FTZ_SLACK; callers that need an
+// upper bound add that constant.
+constexpr float SQRT_FTZ_SLACK = 1.1e-19f;
+__device__ __forceinline__ float sqrt_approx_ftz(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 template <int K>
 __device__ __forceinline__ int sweep_decide_bounded(float m2, float a2, float ar, float m1, float v1, float ce, float t_lo,
@@ -271,6 +304,47 @@ __device__ __forceinline__ int sweep_decide_bounded(float m2, float a2, float ar
     const bool sure_t = (c_lo > 0.0f) & (x_lo > 0.0f) & (c_lo * c_lo > x_hi * t_hi);
     const bool sure_f = (c_hi <= 0.0f) | ((x_lo > 0.0f) & (c_hi * c_hi < x_lo * t_lo));
     return sure_t ? 1 : (sure_f ? 0 : 2);
+}
+
+// Two outputs per instruction (packed fp32x2; this is bound arithmetic, not parity arithmetic: only the inequalities
+// matter).  Same box, with two of its terms replaced by upper bounds that need no absolute values:
+//   T0 (2|m2~| + 4)  <=  T0 (2.001 q~ + 4)            (|m2~| <= q (1 + 1e-5), q~ = sqrt.approx(a2~) within 2^-22 of q)
+//   U4 |x~|          <=  1.001 U4 (|var1| (a2~ + m2~^2) + 1e-8)     (|var2~| = |a2~ - m2~^2| <= a2~ + m2~^2, a2~ >= 0)
+// and q~ from the flush-to-zero square root, whose shortfall on subnormal a2~ is added back where it matters (ec).
+// d0 / d1: 1 = over, 0 = not over, 2 = undecided, for the low / high half.
+template <int K>
+__device__ __forceinline__ void sweep_decide_bounded2(f32x2 m2, f32x2 a2, f32x2 ar, f32x2 m1, f32x2 v1, f32x2 ce, float t_lo,
+                                                      float t_hi, int &d0, int &d1) {
+    using B = Bound<K>;
+    float a20, a21, m10, m11, v10, v11;
+    f2unpack(a2, a20, a21);
+    f2unpack(m1, m10, m11);
+    f2unpack(v1, v10, v11);
+    const f32x2 q = f2pack(sqrt_approx_ftz(a20), sqrt_approx_ftz(a21));     // q~ >= sqrt(a2~)(1 - 2^-22) - SQRT_FTZ_SLACK
+    const f32x2 am1 = f2pack(fabsf(m10), fabsf(m11)), av1 = f2pack(fabsf(v10), fabsf(v11));   // operand modifiers
+    const f32x2 v2 = f2fma(f2neg(m2), m2, a2);
+    const f32x2 cov = f2fma(f2neg(m1), m2, ar);
+    const f32x2 x = f2fma(v1, v2, f2bc(1e-8f));
+    const f32x2 ev = f2fma(f2bc(B::E1), a2, f2mul(f2bc(B::T0), f2fma(f2bc(2.001f), q, f2bc(4.0f))));
+    const f32x2 xa = f2fma(av1, f2fma(m2, m2, a2), f2bc(1e-8f));
+    const f32x2 ex = f2fma(av1, ev, f2fma(f2bc(1.001f * B::U4), xa, f2bc(2e-8f * B::U4)));
+    // ec = ce (q~ + slack) + T0 (|m1| + 4); in ev the slack only meets T0 (2.001 * 1.1e-19 T0 is far below fp32's
+    // resolution of 4 T0) and the |m2~| <= q bound it serves is itself below that resolution when a2~ is subnormal
+    const f32x2 ec = f2fma(ce, q, f2fma(ce, f2bc(SQRT_FTZ_SLACK), f2fma(f2bc(B::T0), am1, f2bc(4.0f * B::T0))));
+    float cl0, cl1, ch0, ch1, xl0, xl1;
+    const f32x2 c_lo = f2sub(cov, ec), c_hi = f2add(cov, ec), x_lo = f2sub(x, ex), x_hi = f2add(x, ex);
+    f2unpack(c_lo, cl0, cl1);
+    f2unpack(c_hi, ch0, ch1);
+    f2unpack(x_lo, xl0, xl1);
+    float cl20, cl21, ch20, ch21, xh0, xh1, xt0, xt1;
+    f2unpack(f2mul(c_lo, c_lo), cl20, cl21);
+    f2unpack(f2mul(c_hi, c_hi), ch20, ch21);
+    f2unpack(f2mul(x_hi, f2bc(t_hi)), xh0, xh1);
+    f2unpack(f2mul(x_lo, f2bc(t_lo)), xt0, xt1);
+    const bool st0 = (cl0 > 0.0f) & (xl0 > 0.0f) & (cl20 > xh0), st1 = (cl1 > 0.0f) & (xl1 > 0.0f) & (cl21 > xh1);
+    const bool sf0 = (ch0 <= 0.0f) | ((xl0 > 0.0f) & (ch20 < xt0)), sf1 = (ch1 <= 0.0f) | ((xl1 > 0.0f) & (ch21 < xt1));
+    d0 = st0 ? 1 : (sf0 ? 0 : 2);
+    d1 = st1 ? 1 : (sf1 ? 0 : 2);
 }
 
 // The reference's chains for ONE output (gx, gy), read straight from the TMA sources in global memory (L2-resident: the
@@ -408,10 +482,27 @@ __global__ void __launch_bounds__(NT, (MODE == N_SWEEP) ? B200D_SEP_MIN_BLOCKS_S
         hphase<K>(sb, s_r, s_h, tid);
         __syncthreads();                                   // h complete
         float as[QY][PX], ass[QY][PX], ars[QY][PX];
+        f32x2 pas[QY][2], pass2[QY][2], pars[QY][2];        // HYB: the same sums, two outputs per register pair
         if (warp_live) {
-            vphase<K>(s_h, tx, ty, as);
-            vphase<K>(s_h + FG::HCH, tx, ty, ass);
-            vphase<K>(s_h + 2 * FG::HCH, tx, ty, ars);
+            if (HYB) {
+                vphase2<K>(s_h, tx, ty, pas);
+                vphase2<K>(s_h + FG::HCH, tx, ty, pass2);
+                vphase2<K>(s_h + 2 * FG::HCH, tx, ty, pars);
+                if (ARITH == A_CHECK) {
+#pragma unroll
+                    for (int q = 0; q < QY; ++q)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            f2unpack(pas[q][j], as[q][2 * j], as[q][2 * j + 1]);
+                            f2unpack(pass2[q][j], ass[q][2 * j], ass[q][2 * j + 1]);
+                            f2unpack(pars[q][j], ars[q][2 * j], ars[q][2 * j + 1]);
+                        }
+                }
+            } else {
+                vphase<K>(s_h, tx, ty, as);
+                vphase<K>(s_h + FG::HCH, tx, ty, ass);
+                vphase<K>(s_h + 2 * FG::HCH, tx, ty, ars);
+            }
         }
         if (ARITH == A_CHECK && warp_live) {
             // diagnostic: observed |separable - chain| over the bound, for the three sums of every output
@@ -451,13 +542,19 @@ __global__ void __launch_bounds__(NT, (MODE == N_SWEEP) ? B200D_SEP_MIN_BLOCKS_S
 #pragma unroll
                 for (int q = 0; q < QY; ++q)
 #pragma unroll
-                    for (int p = 0; p < PX; ++p) {
-                        const bool valid = (vb[q] >> (8 * p + s)) & 1u;
-                        const int dcs = (a.t_lo > 0.0f) ? sweep_decide_bounded<K>(as[q][p], ass[q][p], ars[q][p], m1[q][p],
-                                                                                  v1[q][p], br[q][p], a.t_lo, a.t_hi)
-                                                        : 2;
-                        if ((dcs == 1) & valid) total[q][p] = add(total[q][p], 1.0f);          // :303-304
-                        und |= ((dcs == 2) & valid ? 1u : 0u) << (q * PX + p);
+                    for (int j = 0; j < 2; ++j) {
+                        int dcs[2] = {2, 2};
+                        if (a.t_lo > 0.0f)
+                            sweep_decide_bounded2<K>(pas[q][j], pass2[q][j], pars[q][j], f2pack(m1[q][2 * j], m1[q][2 * j + 1]),
+                                                     f2pack(v1[q][2 * j], v1[q][2 * j + 1]),
+                                                     f2pack(br[q][2 * j], br[q][2 * j + 1]), a.t_lo, a.t_hi, dcs[0], dcs[1]);
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int p = 2 * j + e;
+                            const bool valid = (vb[q] >> (8 * p + s)) & 1u;
+                            if ((dcs[e] == 1) & valid) total[q][p] = add(total[q][p], 1.0f);   // :303-304
+                            und |= ((dcs[e] == 2) & valid ? 1u : 0u) << (q * PX + p);
+                        }
                     }
                 und_all |= (unsigned long long)und << (8 * s);
             }

@@ -43,8 +43,13 @@ struct SampleArgs {
 
 constexpr int SBX = 32, SBY = 8;         // thread block: 32 x 8 pixels
 
-// Sources are processed two at a time through the packed fp32x2 path (project_sample_fast2); an odd count leaves one
-// source to the scalar path.  B200D_SAMPLE_PAIRS=0 builds the all-scalar twin (A/B measurements; identical results).
+// Sources can be processed two at a time through the packed fp32x2 path (project_sample_fast2; an odd count leaves one
+// source to the scalar path; results are bit-identical either way).  Measured on B200 (profiles/microbench/
+// r02_pairs_cmd.sh, r02_pairs_ab2_cmd.sh): the plane sweep's sampling kernel is issue-bound and gains 12 % (56 -> 49 us
+// per plane, sweep 19.9 -> 21.1 Gpix*planes/s); the PatchMatch sampling kernels gain 2-4 % in isolation, but the 4-stream
+// PatchMatch step is bound by FP32-pipe cycles across kernels, where an FFMA2 counts twice, and loses 0.7-1.5 %
+// (181.0 -> 178.4 / 179.6 views/s, reproducible).  So: B200D_SAMPLE_PAIRS = 1 (default) packs the plane sweep only,
+// 2 packs every mode, 0 none (A/B builds).
 #ifndef B200D_SAMPLE_PAIRS
 #define B200D_SAMPLE_PAIRS 1
 #endif
@@ -134,17 +139,18 @@ __global__ void __launch_bounds__(SBX *SBY, B200D_SAMPLE_MIN_BLOCKS) sample_kern
             out[(size_t)(s + h) * a.map_stride] = smp[h];
         }
     };
+    constexpr bool PAIRS = B200D_SAMPLE_PAIRS == 2 || (B200D_SAMPLE_PAIRS == 1 && CAND == C_PLANE);
     if (NS > 0) {
 #pragma unroll
         for (int s = 0; s + 1 < NS; s += 2) {
-            if (B200D_SAMPLE_PAIRS) two_sources(s);
+            if (PAIRS) two_sources(s);
             else { one_source(s); one_source(s + 1); }
         }
         if (NS & 1) one_source(NS - 1);
     } else {
         const int S = a.cams.n_src;
         int s = 0;
-        if (B200D_SAMPLE_PAIRS)
+        if (PAIRS)
             for (; s + 1 < S; s += 2) two_sources(s);
 #pragma unroll 2
         for (; s < S; ++s) one_source(s);
