@@ -6,6 +6,8 @@
 //   ncc_kernel     (ncc_kernels.cuh)     TMA-fed tiles -> K x K window sums (FFMA2) -> NCC -> select
 // The sampled images sit in an L2-sized scratch between the two.
 #include <atomic>
+#include <fcntl.h>
+#include <unistd.h>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -860,14 +862,83 @@ int b200d_prepare_image(const uint8_t *d_bgr, int H, int W, int nh, int nw, cons
 
 // Host-side: ASCII PLY in the reference's exact format (src/core/utils.py:8-37): "%.6f %.6f %.6f %d %d %d\n".
 // The reference formats one point per Python iteration.  Here blocks of points are formatted in parallel (OpenMP:
-// every thread snprintf's a contiguous run of vertices into its own buffer) and the buffers are written in order, so
-// the file is byte-identical to the sequential writer's.
+// every thread formats a contiguous run of vertices into its own buffer) and every thread then writes its run at the
+// file offset the run lengths imply (pwrite), so the file is byte-identical to the sequential writer's.
+//
+// "%.6f" of a double, exactly as the C library / Python print it: the decimal expansion of the binary value, rounded
+// to six places, ties to even.  x = m 2^e with a 53-bit m, so for e < 0 the scaled value m 10^6 / 2^-e is a 128-bit
+// integer division by a power of two: quotient, remainder against one half, done -- no floating point involved, ~10x
+// faster than snprintf.  Returns NULL for what it does not cover (inf, NaN, |x| >= 2^52, results beyond 64 bits);
+// the caller then uses snprintf for that value.
+static inline char *fmt_u64(char *p, uint64_t v) {
+    char tmp[20];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+static inline char *fmt_fixed6(char *p, double x) {
+    uint64_t bits;
+    memcpy(&bits, &x, sizeof(bits));
+    const int ex = (int)((bits >> 52) & 0x7ff);
+    uint64_t n = 0;                                       // round_half_even(|x| * 10^6)
+    if (ex == 0x7ff) return nullptr;                      // inf / NaN
+    if (ex != 0) {                                        // zero and subnormals print as 0.000000
+        const uint64_t man = (bits & ((1ull << 52) - 1)) | (1ull << 52);
+        const int sh = 1075 - ex;                         // |x| = man / 2^sh
+        if (sh <= 0) return nullptr;                      // |x| >= 2^52
+        if (sh < 128) {                                   // otherwise |x| 10^6 < 2^73 / 2^128: rounds to 0
+            const unsigned __int128 P = (unsigned __int128)man * 1000000u;
+            unsigned __int128 q = P >> sh;
+            const unsigned __int128 rem = P - (q << sh), half = (unsigned __int128)1 << (sh - 1);
+            if (rem > half || (rem == half && ((uint64_t)q & 1u))) ++q;
+            if (q >> 64) return nullptr;
+            n = (uint64_t)q;
+        }
+    }
+    if (bits >> 63) *p++ = '-';
+    p = fmt_u64(p, n / 1000000u);
+    *p++ = '.';
+    uint32_t fr = (uint32_t)(n % 1000000u);
+    for (int i = 5; i >= 0; --i) { p[i] = (char)('0' + fr % 10); fr /= 10; }
+    return p + 6;
+}
+// one coordinate + the separator that follows it; falls back to snprintf for the values fmt_fixed6 declines
+static inline size_t fmt_coord(std::vector<char> &buf, size_t pos, double x) {
+    if (buf.size() < pos + 64) buf.resize(buf.size() * 2 + (1 << 16));
+    char *p = fmt_fixed6(buf.data() + pos, x);
+    if (!p) {
+        int w = snprintf(buf.data() + pos, buf.size() - pos, "%.6f", x);
+        if (w < 0) w = 0;
+        if ((size_t)w + 2 >= buf.size() - pos) {          // astronomically large coordinate: grow and redo
+            buf.resize(buf.size() * 2 + (size_t)w + 1024);
+            w = snprintf(buf.data() + pos, buf.size() - pos, "%.6f", x);
+        }
+        p = buf.data() + pos + w;
+    }
+    *p++ = ' ';
+    return (size_t)(p - buf.data());
+}
+
+static bool write_all_at(int fd, const char *data, size_t len, off_t at) {
+    while (len) {
+        const ssize_t w = pwrite(fd, data, len, at);
+        if (w <= 0) return false;
+        data += w; len -= (size_t)w; at += w;
+    }
+    return true;
+}
+
 int b200d_write_ply_ascii(const char *path, const double *points, const uint8_t *colors, int64_t n) {
     if (!path || n < 0 || (n > 0 && (!points || !colors))) return fail(B200D_ERR_ARG, "bad argument");
-    FILE *f = fopen(path, "wb");
-    if (!f) return fail(B200D_ERR_ARG, "cannot open output file");
-    fprintf(f, "ply\nformat ascii 1.0\nelement vertex %lld\nproperty float x\nproperty float y\nproperty float z\n"
-               "property uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n", (long long)n);
+    const int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return fail(B200D_ERR_ARG, "cannot open output file");
+    char header[256];
+    const int hl = snprintf(header, sizeof(header),
+                            "ply\nformat ascii 1.0\nelement vertex %lld\nproperty float x\nproperty float y\nproperty float z\n"
+                            "property uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n", (long long)n);
+    bool bad = !write_all_at(fd, header, (size_t)hl, 0);
+    off_t filepos = hl;
     // Threads: the cores this process may run on (affinity mask), not OMP_NUM_THREADS -- launchers such as torchrun
     // export OMP_NUM_THREADS=1 for every rank, yet only rank 0 writes the cloud.  B200D_PLY_THREADS overrides.
     int T = 1;
@@ -878,40 +949,43 @@ int b200d_write_ply_ascii(const char *path, const double *points, const uint8_t 
     if (T > 64) T = 64;
 #endif
     const int64_t BLOCK = 1 << 22;                       // vertices formatted per round (bounds the staging memory)
-    // "%.6f" of a double prints at most 1 + 309 + 1 + 6 characters; coordinates of a cloud are a few digits, so
-    // reserve generously per vertex and let snprintf report the length actually used
     std::vector<std::vector<char>> bufs((size_t)T);
     std::vector<size_t> used((size_t)T);
-    bool bad = false;
+    std::vector<off_t> at((size_t)T);
+    std::atomic<bool> wbad(false);
     for (int64_t b0 = 0; b0 < n && !bad; b0 += BLOCK) {
         const int64_t bn = (n - b0 < BLOCK) ? n - b0 : BLOCK;
         const int64_t per = (bn + T - 1) / T;
-#pragma omp parallel for schedule(static, 1) num_threads(T)
-        for (int t = 0; t < T; ++t) {
-            const int64_t i0 = b0 + (int64_t)t * per, i1 = (i0 + per < b0 + bn) ? i0 + per : b0 + bn;
-            std::vector<char> &buf = bufs[(size_t)t];
-            size_t pos = 0;
-            for (int64_t i = i0; i < i1; ++i) {
-                if (buf.size() < pos + 1024) buf.resize(buf.size() * 2 + (1 << 16));
-                int w = snprintf(buf.data() + pos, buf.size() - pos, "%.6f %.6f %.6f %d %d %d\n", points[3 * i],
-                                 points[3 * i + 1], points[3 * i + 2], (int)colors[3 * i], (int)colors[3 * i + 1],
-                                 (int)colors[3 * i + 2]);
-                if (w < 0) w = 0;
-                if ((size_t)w >= buf.size() - pos) {                     // astronomically large coordinate: grow and redo
-                    buf.resize(buf.size() * 2 + (size_t)w + 1024);
-                    w = snprintf(buf.data() + pos, buf.size() - pos, "%.6f %.6f %.6f %d %d %d\n", points[3 * i],
-                                 points[3 * i + 1], points[3 * i + 2], (int)colors[3 * i], (int)colors[3 * i + 1],
-                                 (int)colors[3 * i + 2]);
+#pragma omp parallel num_threads(T)
+        {
+#pragma omp for schedule(static, 1)
+            for (int t = 0; t < T; ++t) {
+                const int64_t i0 = b0 + (int64_t)t * per, i1 = (i0 + per < b0 + bn) ? i0 + per : b0 + bn;
+                std::vector<char> &buf = bufs[(size_t)t];
+                size_t pos = 0;
+                for (int64_t i = i0; i < i1; ++i) {
+                    pos = fmt_coord(buf, pos, points[3 * i]);
+                    pos = fmt_coord(buf, pos, points[3 * i + 1]);
+                    pos = fmt_coord(buf, pos, points[3 * i + 2]);
+                    if (buf.size() < pos + 16) buf.resize(buf.size() * 2 + (1 << 16));
+                    char *p = buf.data() + pos;
+                    p = fmt_u64(p, colors[3 * i]);     *p++ = ' ';
+                    p = fmt_u64(p, colors[3 * i + 1]); *p++ = ' ';
+                    p = fmt_u64(p, colors[3 * i + 2]); *p++ = '\n';
+                    pos = (size_t)(p - buf.data());
                 }
-                pos += (size_t)w;
+                used[(size_t)t] = pos;
             }
-            used[(size_t)t] = pos;
+            // implicit barrier: all run lengths are known; one thread lays the runs out, then everybody writes its own
+#pragma omp single
+            for (int t = 0; t < T; ++t) { at[(size_t)t] = filepos; filepos += (off_t)used[(size_t)t]; }
+#pragma omp for schedule(static, 1)
+            for (int t = 0; t < T; ++t)
+                if (used[(size_t)t] && !write_all_at(fd, bufs[(size_t)t].data(), used[(size_t)t], at[(size_t)t])) wbad = true;
         }
-        for (int t = 0; t < T && !bad; ++t)
-            if (used[(size_t)t] && fwrite(bufs[(size_t)t].data(), 1, used[(size_t)t], f) != used[(size_t)t]) bad = true;
+        bad = bad || wbad.load();
     }
-    bad = bad || ferror(f) != 0;
-    if (fclose(f) != 0 || bad) return fail(B200D_ERR_ARG, "write failed");
+    if (close(fd) != 0 || bad) return fail(B200D_ERR_ARG, "write failed");
     return B200D_OK;
 }
 

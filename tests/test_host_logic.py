@@ -164,6 +164,13 @@ def test_parallel_ply_writer_is_order_and_byte_exact(tmp_path, n):
         pts[3] = [1e300, -1e300, 1e-300]
         pts[4] = [np.inf, -np.inf, np.nan]
         pts[5] = [-0.0, 0.4999995, -0.0000005]
+        # the writer's own exact "%.6f" (128-bit integer rounding): binary ties round to even, subnormals print as zero,
+        # values it declines (>= 2^52, beyond 64 bits after scaling) go through snprintf
+        pts[6] = [0.0078125, -0.0078125, 0.0234375]
+        pts[7] = [2.5e-6, 3.5e-6, 999999.9999995]
+        pts[8] = [4503599627370496.0, 1e12, 1.9e13]
+        pts[9] = [5e-324, -2.2250738585072014e-308, 0.9999995]
+        pts[10] = [2.0 ** -21, -(2.0 ** -20), 2.0 ** -75]
     col = rng.integers(0, 256, size=(n, 3)).astype(np.uint8)
     out = tmp_path / 'p.ply'
     save_ply(pts, col, str(out))
