@@ -3,7 +3,12 @@
 The reference is single-process (no distributed code).  Its dense stage treats every
 reference view independently, so the path shards by views with no data-path collective:
 
-    rank r computes views[r::world]        (round-robin keeps turntable neighbours on different GPUs)
+    rank r computes a CONTIGUOUS block of the sorted view list (`shard_positions`: sizes differ by at most one)
+
+Blocks, not round-robin: a view's sources are its neighbours on the camera path, so consecutive views share most of
+their source images and a rank only has to hold (upload, prepare) its block plus a margin -- 49 instead of 150
+photographs per GPU for 200 turntable views on 8 GPUs, which is what bounded that job.  The makespan
+(ceil(n / world) views) is the same for both policies; the map all-gather needs no re-interleaving with blocks.
 
 Exchanges:
   * `peer_cloud` / `peer_fence` -- the preferred cloud gather on NVLink boxes: rank 0's output buffers are symmetric
@@ -33,16 +38,29 @@ def world() -> Tuple[int, int]:
     return 0, 1
 
 
-def shard_views(views: Sequence[int], rank: int = None, world_size: int = None) -> List[int]:
-    """Views owned by `rank`: views[rank::world]."""
+def shard_positions(n_positions: int, rank: int = None, world_size: int = None) -> range:
+    """Positions (indices into the sorted view list) owned by `rank`: a contiguous block; the first n % world ranks
+    hold one position more than the others."""
     if rank is None or world_size is None:
         rank, world_size = world()
-    return list(views)[rank::world_size]
+    q, r = divmod(int(n_positions), int(world_size))
+    start = rank * q + min(rank, r)
+    return range(start, start + q + (1 if rank < r else 0))
 
 
-def owner_of(position: int, world_size: int) -> int:
-    """Rank that owns the view at `position` of the sorted view list."""
-    return position % world_size
+def shard_views(views: Sequence[int], rank: int = None, world_size: int = None) -> List[int]:
+    """Views owned by `rank` (its block of the given list)."""
+    views = list(views)
+    return [views[p] for p in shard_positions(len(views), rank, world_size)]
+
+
+def owner_of(position: int, world_size: int, n_positions: int) -> int:
+    """Rank that owns the view at `position` of the sorted view list of `n_positions` views."""
+    q, r = divmod(int(n_positions), int(world_size))
+    head = r * (q + 1)                                    # positions held by the ranks with q + 1 views
+    if position < head:
+        return position // (q + 1)
+    return r + (position - head) // q
 
 
 def exchange_counts(n_positions: int, local_counts: Dict[int, int], device: torch.device) -> List[int]:
@@ -76,7 +94,7 @@ def gather_into(counts: Sequence[int], local: Dict[int, Tuple[torch.Tensor, torc
     ops, off = [], 0
     for pos, m in enumerate(counts):
         m = int(m)
-        owner = owner_of(pos, ws)
+        owner = owner_of(pos, ws, len(counts))
         if m and owner != 0:
             if rank == 0:
                 ops += [dist.P2POp(dist.irecv, out_points[off:off + m], owner),
@@ -99,7 +117,10 @@ class _PeerCloud:
         if n <= self.cap:
             return
         import torch.distributed._symmetric_memory as symm_mem
-        cap = max(int(n * 1.25) + 1024, 1 << 20)
+        # Sized for a 180 GB GPU, not for the first cloud seen: at least 16 M points (512 MB), then doubling.  A
+        # (re)allocation is a collective rendezvous that costs 0.1-2 s -- measured 0.65 s inside a 3.5 s 200-view job
+        # when a small first reconstruction had left a 1 M-point buffer behind (profiles/r02s3_full4k_*.json).
+        cap = max(int(n * 1.25) + 1024, 2 * self.cap, 1 << 24)
         # one allocation, one rendezvous: 24 bytes of coordinates + 3 bytes of colour per point (+ slack for alignment)
         self.raw = symm_mem.empty(cap * 32, dtype=torch.uint8, device=self.device)
         self.handle = symm_mem.rendezvous(self.raw, dist.group.WORLD)
@@ -177,14 +198,14 @@ def gather_point_clouds(views: Sequence[int], local: Dict[int, Tuple[torch.Tenso
     n = len(views)
     counts = torch.zeros(n, dtype=torch.int64, device=device)
     for pos, v in enumerate(views):
-        if owner_of(pos, ws) == rank and v in local:
+        if owner_of(pos, ws, n) == rank and v in local:
             counts[pos] = local[v][0].shape[0]
     if ws > 1:
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)          # every position has exactly one owner
     counts_h = counts.cpu().tolist()
 
     def mine(r):
-        return [pos for pos in range(n) if owner_of(pos, ws) == r]
+        return list(shard_positions(n, r, ws))
 
     def pack(r_views):
         pts = [local[views[p]][0] for p in r_views if counts_h[p] > 0]
@@ -216,11 +237,11 @@ def gather_point_clouds(views: Sequence[int], local: Dict[int, Tuple[torch.Tenso
     if rank != 0:
         return (torch.zeros((0, 3), dtype=torch.float64, device=device),
                 torch.zeros((0, 3), dtype=torch.uint8, device=device))
-    # re-interleave: position p lives in its owner's buffer after that owner's earlier positions
+    # position p lives in its owner's buffer after that owner's earlier positions
     offs = {r: 0 for r in range(ws)}
     out_p, out_c = [], []
     for pos in range(n):
-        r, m = owner_of(pos, ws), counts_h[pos]
+        r, m = owner_of(pos, ws, n), counts_h[pos]
         if m:
             bp, bc = per_rank[r]
             out_p.append(bp[offs[r]:offs[r] + m])
@@ -243,7 +264,7 @@ def all_gather_maps(views: Sequence[int], local: Dict[int, torch.Tensor], shape:
     n = len(views)
     per = (n + ws - 1) // ws
     block = torch.zeros((per,) + tuple(shape), dtype=dtype, device=device)
-    for k, pos in enumerate(range(rank, n, ws)):
+    for k, pos in enumerate(shard_positions(n, rank, ws)):
         v = views[pos]
         if v in local:
             block[k].copy_(local[v])
@@ -253,6 +274,7 @@ def all_gather_maps(views: Sequence[int], local: Dict[int, torch.Tensor], shape:
         full = torch.empty((ws * per,) + tuple(shape), dtype=dtype, device=device)
         dist.all_gather_into_tensor(full, block)
     out = {}
-    for pos, v in enumerate(views):
-        out[v] = full[owner_of(pos, ws) * per + pos // ws]
+    for r in range(ws):
+        for k, pos in enumerate(shard_positions(n, r, ws)):
+            out[views[pos]] = full[r * per + k]
     return out

@@ -117,14 +117,14 @@ class DenseStereoReconstructor:
         step = max(1, n_cameras // max_pairs)                    # reference :100-101
         ref_indices = camera_indices[::step]
         print(f"\nProcessing {len(ref_indices)} reference views...")
-        # Reference views are independent: shard them round-robin over the ranks of an initialised
+        # Reference views are independent: shard them in contiguous blocks over the ranks of an initialised
         # torch.distributed job and keep `views_in_flight` of this rank's views on separate streams.
         from b200dense import dist as bdist
         rank, ws = bdist.world()
         eng = self.engine
         Kinv = np.linalg.inv(self.K_scaled)
         plan = []
-        for pos in range(rank, len(ref_indices), ws):
+        for pos in bdist.shard_positions(len(ref_indices), rank, ws):
             ref_idx = ref_indices[pos]
             neighbors = self._find_neighbors(ref_idx, camera_indices, poses, k=self.num_neighbors)
             if len(neighbors) >= 2:

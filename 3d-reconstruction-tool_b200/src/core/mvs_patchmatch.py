@@ -167,7 +167,7 @@ class PatchMatchMVS:
                     sparse_points: np.ndarray = None) -> Tuple[np.ndarray, np.ndarray]:
         """Depth maps for every posed view, fused into one cloud (reference :72-139).
 
-        Views are independent, so they are (a) sharded round-robin over the ranks of an initialised
+        Views are independent, so they are (a) sharded in contiguous blocks over the ranks of an initialised
         torch.distributed job (one process per GPU; without one this is a single-GPU run) and (b) kept
         `views_in_flight` at a time on separate streams of each GPU.  Rank 0 returns the fused and filtered
         cloud in the reference's order (sorted views, row-major pixels); other ranks return (0,3) arrays.
@@ -203,7 +203,7 @@ class PatchMatchMVS:
         ready = self._stage_images(proc_images, [])             # opens the copy stream; images follow view by view
         # host-drawn random numbers must be consumed in view order -> one view at a time in that mode
         in_flight = 1 if self.rng == 'torch' else self.views_in_flight
-        mine = [(pos, cam_indices[pos]) for pos in range(rank, n_cams, ws)]
+        mine = [(pos, cam_indices[pos]) for pos in bdist.shard_positions(n_cams, rank, ws)]
         if self.schedule == 'viewprop':
             plan = []
             for pos, ref_idx in mine:

@@ -300,11 +300,13 @@ def main():
     ARITH = _cabi.FAST if a.arith == 'fast' else _cabi.PARITY
 
     V, H, W = a.views_per_gpu, a.height, a.width
-    ref_views = list(range(N_SCENE_VIEWS))[rank::world][:V]
-    all_views = sorted(v for rk in range(world) for v in list(range(N_SCENE_VIEWS))[rk::world][:V])
+    # weak scaling: V consecutive views of the turntable per GPU (the library's block sharding, b200dense/dist.py)
+    assert V * world <= N_SCENE_VIEWS, 'views-per-gpu x gpus exceeds the synthetic turntable'
+    all_views = list(range(V * world))
+    ref_views = bdist.shard_views(all_views, rank, world)
     pos_of = {v: p for p, v in enumerate(all_views)}
     # gather check (N>1): rank 0 recomputes the first view owned by rank 1 -> it needs that view's images too
-    check_view = all_views[1] if world > 1 else None
+    check_view = bdist.shard_views(all_views, 1, world)[0] if world > 1 else None
     sc, poses, pm, srcs, need = scene_for(a, ref_views, dev, extra_views=[check_view] if (world > 1 and rank == 0) else [])
     gray = gray_f32(sc)
     d_gray = {i: eng.to_device(gray[i]) for i in need}

@@ -33,13 +33,13 @@ def _worker(rank, ws, port, q):
     dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=ws)
     try:
         mine = bdist.shard_views(VIEWS)
-        assert mine == VIEWS[rank::ws]
+        my_pos = list(bdist.shard_positions(len(VIEWS)))
+        assert mine == [VIEWS[p] for p in my_pos] and my_pos == ([0, 1, 2, 3] if rank == 0 else [4, 5, 6])   # blocks
         local = {v: _fake_cloud(v, COUNTS[v]) for v in mine if v != 8}     # view 8 missing entirely
         pts, col = bdist.gather_point_clouds(VIEWS, local, torch.device('cpu'))
         maps = bdist.all_gather_maps(VIEWS, {v: torch.full((3, 4), float(v)) for v in mine}, (3, 4), torch.device('cpu'))
         ok_maps = all(torch.equal(maps[v], torch.full((3, 4), float(v))) for v in VIEWS)
         # the copy-free gather reconstruct() uses: counts exchanged once, rank 0 receives straight into final slices
-        my_pos = list(range(rank, len(VIEWS), ws))
         counts = bdist.exchange_counts(len(VIEWS), {p: COUNTS[VIEWS[p]] for p in my_pos}, torch.device('cpu'))
         assert counts == [COUNTS[v] for v in VIEWS]
         offs = np.concatenate([[0], np.cumsum(counts)])
@@ -89,7 +89,7 @@ def test_single_process_paths():
     import sys
     from b200dense import dist as bdist
     assert bdist.world() == (0, 1)
-    assert bdist.shard_views([4, 5, 6], 1, 2) == [5]
+    assert bdist.shard_views([4, 5, 6], 1, 2) == [6] and bdist.shard_views([4, 5, 6], 0, 2) == [4, 5]
     local = {v: _fake_cloud(v, COUNTS[v]) for v in VIEWS}
     pts, col = bdist.gather_point_clouds(VIEWS, local, torch.device('cpu'))
     assert pts.shape[0] == sum(COUNTS.values()) and col.dtype == torch.uint8
@@ -101,4 +101,10 @@ def test_single_process_paths():
     assert bdist.exchange_counts(4, {0: 3, 2: 5}, torch.device('cpu')) == [3, 0, 5, 0]
     bdist.gather_into([3, 0, 5, 0], {}, None, None)
     assert bdist.peer_cloud(torch.device('cpu'), 100) is None
-    assert bdist.owner_of(5, 4) == 1
+    # contiguous blocks whose sizes differ by at most one; owner_of is the inverse of shard_positions for any (n, world)
+    for n in (0, 1, 3, 7, 8, 9, 64, 200):
+        for ws in (1, 2, 3, 4, 8):
+            blocks = [list(bdist.shard_positions(n, r, ws)) for r in range(ws)]
+            assert sum(blocks, []) == list(range(n))
+            assert max(map(len, blocks)) - min(map(len, blocks)) <= 1
+            assert all(bdist.owner_of(p, ws, n) == r for r in range(ws) for p in blocks[r])
