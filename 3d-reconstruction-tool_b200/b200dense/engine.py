@@ -7,6 +7,7 @@ There is no CPU path: constructing a DenseEngine without CUDA raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -82,6 +83,51 @@ class PinnedPool:
 PINNED = PinnedPool()
 
 
+class UploadRing:
+    """Pageable host array -> pooled page-locked slot (memcpy on a few threads; NumPy releases the GIL) -> async DMA.
+
+    `tensor.to(device)` from a caller's pageable array goes through the driver's staging path, which is synchronous for
+    the host thread and must first wait for whatever precedes it on the stream.  In isolation both paths are fast (10.9
+    vs 28 GB/s, profiles/microbench/r02s3_upload_ab.py), but inside a 200-view 4K reconstruction, where the same thread
+    also has to keep four views' worth of kernels enqueued, the ring is worth 5-20 % and removes most of the run-to-run
+    spread: 5.35 / 5.34 s against 5.64 / 6.63 s on the same box (profiles/microbench/r02s3_upload3_cmd.sh).  Arrays that
+    are page-locked already (the batch API's staging buffers) are DMA'd directly: sending those through the ring cost
+    30 % of the e2e rate.  B200D_UPLOAD=direct disables the ring."""
+    SLOTS = 4
+
+    def __init__(self):
+        from concurrent.futures import ThreadPoolExecutor
+        self._slots, self._events, self._next = [None] * self.SLOTS, [None] * self.SLOTS, 0
+        self._pool, self._threads = ThreadPoolExecutor(max_workers=8), 4
+
+    def _executor(self):
+        return self._pool
+
+    def upload(self, a, tdtype, device):
+        k = self._next % self.SLOTS
+        self._next += 1
+        if self._events[k] is not None:
+            self._events[k].synchronize()
+        n = a.nbytes
+        buf = self._slots[k]
+        if buf is None or buf.numel() < n:
+            buf = self._slots[k] = torch.empty(max(n, 1 << 25), dtype=torch.uint8, pin_memory=True)
+        dst, src = buf[:n].numpy(), a.reshape(-1).view(np.uint8)
+        if self._threads == 1:
+            np.copyto(dst, src)
+        else:
+            step = -(-n // self._threads)
+            list(self._pool.map(lambda i: np.copyto(dst[i:i + step], src[i:i + step]), range(0, n, step)))
+        out = torch.empty(a.shape, dtype=tdtype, device=device)
+        out.copy_(buf[:n].view(tdtype).view(a.shape), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        self._events[k] = ev
+        return out
+
+
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     if t is None:
         return None
@@ -139,7 +185,13 @@ class DenseEngine:
         return buf
 
     def to_device(self, a: np.ndarray, dtype=torch.float32) -> torch.Tensor:
-        t = torch.from_numpy(np.ascontiguousarray(a))
+        a = np.ascontiguousarray(a)
+        t = torch.from_numpy(a)
+        if (os.environ.get('B200D_UPLOAD', 'ring') == 'ring' and t.dtype == dtype and a.nbytes >= (1 << 20)
+                and torch.device(self.device).type == 'cuda' and not t.is_pinned()):
+            if getattr(self, '_upload_ring', None) is None:
+                self._upload_ring = UploadRing()
+            return self._upload_ring.upload(a, dtype, torch.device(self.device))
         return t.to(self.device, dtype=dtype, non_blocking=True).contiguous()
 
     @staticmethod
