@@ -51,16 +51,18 @@ class CameraPose:
 
 
 def load_calibration(calibration_path: str) -> Camera:
-    """Read `mtx` / `dist` from a calibration .npz (dist padded to 5 coefficients)."""
-    path = Path(calibration_path)
-    if not path.exists():
-        raise FileNotFoundError(f"Calibration file not found: {path}")
-    with np.load(str(path)) as data:
-        K = data['mtx'].astype(np.float64)
-        dist = data['dist'].astype(np.float64).ravel()
-    if dist.size < 5:
-        dist = np.pad(dist, (0, 5 - dist.size))
-    print(f"Loaded calibration from {path.name}")
-    print(f"  Focal length: fx={K[0,0]:.1f}, fy={K[1,1]:.1f}")
-    print(f"  Principal point: cx={K[0,2]:.1f}, cy={K[1,2]:.1f}")
-    return Camera(K=K, dist=dist)
+    """Camera from a calibration .npz (keys `mtx`, `dist`; fewer than five distortion coefficients are zero-padded).
+    Same banner lines and the same FileNotFoundError text as the reference (src/core/camera.py:111-138)."""
+    src = Path(calibration_path)
+    try:
+        with np.load(str(src)) as npz:
+            mtx = np.asarray(npz['mtx'], dtype=np.float64)
+            coeffs = np.asarray(npz['dist'], dtype=np.float64).reshape(-1)
+    except FileNotFoundError:
+        raise FileNotFoundError(f"Calibration file not found: {src}") from None
+    cam = Camera(K=mtx, dist=np.concatenate([coeffs, np.zeros(max(0, 5 - coeffs.size))]))
+    for line in (f"Loaded calibration from {src.name}",
+                 f"  Focal length: fx={cam.fx:.1f}, fy={cam.fy:.1f}",
+                 f"  Principal point: cx={cam.cx:.1f}, cy={cam.cy:.1f}"):
+        print(line)
+    return cam
