@@ -218,10 +218,11 @@ int launch_ncc_k(int patch, const NccArgs &a, cudaStream_t st) {
 template <int K, int MODE, int ARITH>
 int launch_sep(const NccArgs &a, cudaStream_t st) {
     static std::atomic<uint64_t> configured{0};
-    TRY(ensure_smem(ncc_sep_kernel<K, MODE, ARITH>, configured, FGeo<K>::smem_bytes));
+    constexpr size_t smem = SepCfg<K, MODE, ARITH>::smem_bytes;
+    TRY(ensure_smem(ncc_sep_kernel<K, MODE, ARITH>, configured, smem));
     ProfScope prof((ARITH == A_FAST ? 10000 : ARITH == A_HYBRID ? 20000 : 30000) + MODE * 100 + K, st);
     const dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, 1);
-    ncc_sep_kernel<K, MODE, ARITH><<<grid, NT, FGeo<K>::smem_bytes, st>>>(a);
+    ncc_sep_kernel<K, MODE, ARITH><<<grid, NT, smem, st>>>(a);
     return cuda_check(cudaGetLastError(), "ncc_sep_kernel launch");
 }
 

@@ -416,8 +416,30 @@ __device__ unsigned long long g_sweep_fallbacks;
 #ifndef B200D_SEP_MIN_BLOCKS_PM
 #define B200D_SEP_MIN_BLOCKS_PM 2
 #endif
+// Bounded plane sweep with ONE sample stage (B200D_SEP_ONE_STAGE = 1, the default): only the H phase reads the sampled
+// tile, so the next neighbour's tile is fetched into the same buffer as soon as the H phase is over (first CTA barrier)
+// and arrives while the V phase and the decision run -- a second stage buys nothing there, and without it a CTA needs
+// 51 KB instead of 62 KB (K = 7), which together with B200D_SEP_MIN_BLOCKS_ONE = 4 (64 registers; the eight running
+// counts packed into one register keep the spills at 8 words) lets a fourth CTA reside on the SM.  The kernel is
+// latency-bound at 24 warps per SM (profiles/r02s3_ncu_sweep.txt).  Measured (profiles/microbench/r02s3_onestage_cmd.sh):
+// isolated launch 73.9 -> 72.5 us, sweep with two views in flight 21.17 -> 22.04 Gpix*planes/s (the smaller footprint
+// also leaves more L1 to the co-resident sampling kernel); bit-identical results.  0 = two stages, 3 CTAs (A/B twin).
+#ifndef B200D_SEP_ONE_STAGE
+#define B200D_SEP_ONE_STAGE 1
+#endif
+#ifndef B200D_SEP_MIN_BLOCKS_ONE
+#define B200D_SEP_MIN_BLOCKS_ONE 4
+#endif
 template <int K, int MODE, int ARITH>
-__global__ void __launch_bounds__(NT, (MODE == N_SWEEP) ? B200D_SEP_MIN_BLOCKS_SWEEP : B200D_SEP_MIN_BLOCKS_PM) ncc_sep_kernel(const __grid_constant__ NccArgs a) {
+struct SepCfg {
+    static constexpr bool one_stage = B200D_SEP_ONE_STAGE && MODE == N_SWEEP && ARITH == A_HYBRID;
+    static constexpr int nbuf = one_stage ? 2 : 3;                        // reference + sample stage(s)
+    static constexpr size_t smem_bytes = nbuf * (size_t)Geo<K>::buf_bytes + FGeo<K>::h_bytes + 64;
+    static constexpr int min_blocks = one_stage ? B200D_SEP_MIN_BLOCKS_ONE
+                                                : (MODE == N_SWEEP ? B200D_SEP_MIN_BLOCKS_SWEEP : B200D_SEP_MIN_BLOCKS_PM);
+};
+template <int K, int MODE, int ARITH>
+__global__ void __launch_bounds__(NT, SepCfg<K, MODE, ARITH>::min_blocks) ncc_sep_kernel(const __grid_constant__ NccArgs a) {
     using G = Geo<K>;
     using FG = FGeo<K>;
     constexpr int HALF = G::HALF;
@@ -426,8 +448,10 @@ __global__ void __launch_bounds__(NT, (MODE == N_SWEEP) ? B200D_SEP_MIN_BLOCKS_S
     extern __shared__ __align__(128) unsigned char sm[];
     constexpr int BUF = G::buf_bytes / sizeof(float);
     float *s_r = reinterpret_cast<float *>(sm);
-    float *s_h = reinterpret_cast<float *>(sm + 3 * G::buf_bytes);           // [3][HR][TW]
-    uint64_t *bar = reinterpret_cast<uint64_t *>(sm + 3 * G::buf_bytes + FG::h_bytes);   // [0],[1]: stages ; [2]: reference
+    constexpr bool ONE = SepCfg<K, MODE, ARITH>::one_stage;                  // one sample stage (see B200D_SEP_ONE_STAGE)
+    constexpr int NBUF = SepCfg<K, MODE, ARITH>::nbuf;
+    float *s_h = reinterpret_cast<float *>(sm + NBUF * G::buf_bytes);        // [3][HR][TW]
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sm + NBUF * G::buf_bytes + FG::h_bytes);   // [0],[1]: stages ; [2]: reference
 
     const int tid = threadIdx.x;
     const int tx = tid % NTX, ty = tid / NTX;
@@ -447,7 +471,7 @@ __global__ void __launch_bounds__(NT, (MODE == N_SWEEP) ? B200D_SEP_MIN_BLOCKS_S
         tma_load_2d(s_r, &a.tm_r, &bar[2], cx, cy);
         mbar_expect_tx(&bar[0], G::tile_bytes);
         tma_load_2d(s_r + BUF, &a.tm_s[0], &bar[0], cx, cy);
-        if (S > 1) {
+        if (!ONE && S > 1) {
             mbar_expect_tx(&bar[1], G::tile_bytes);
             tma_load_2d(s_r + 2 * BUF, &a.tm_s[1], &bar[1], cx, cy);
         }
@@ -455,6 +479,8 @@ __global__ void __launch_bounds__(NT, (MODE == N_SWEEP) ? B200D_SEP_MIN_BLOCKS_S
 
     float m1[QY][PX], v1[QY][PX], br[QY][PX], total[QY][PX];
     unsigned vb[QY], cnt = 0;
+    unsigned tcnt = 0;                                     // HYB: the eight running counts (0 .. 8 each), four bits per output --
+                                                           // integers are exact, and one register instead of eight
 #pragma unroll
     for (int q = 0; q < QY; ++q) {
         vb[q] = 0;
@@ -476,11 +502,15 @@ __global__ void __launch_bounds__(NT, (MODE == N_SWEEP) ? B200D_SEP_MIN_BLOCKS_S
     unsigned long long und_all = 0;                        // A_HYBRID: bit 8 s + (q PX + p) = output still undecided
     mbar_wait(&bar[2], 0);
     for (int s = 0; s < S; ++s) {
-        const int st = s & 1;
-        mbar_wait(&bar[st], (s >> 1) & 1);
+        const int st = ONE ? 0 : (s & 1);
+        mbar_wait(&bar[st], ONE ? (s & 1) : ((s >> 1) & 1));
         const float *sb = s_r + (1 + st) * BUF;
         hphase<K>(sb, s_r, s_h, tid);
         __syncthreads();                                   // h complete
+        if (ONE && tid == 0 && s + 1 < S) {                // nothing reads the sample tile any more: fetch the next one
+            mbar_expect_tx(&bar[0], G::tile_bytes);
+            tma_load_2d(s_r + BUF, &a.tm_s[s + 1], &bar[0], cx, cy);
+        }
         float as[QY][PX], ass[QY][PX], ars[QY][PX];
         f32x2 pas[QY][2], pass2[QY][2], pars[QY][2];        // HYB: the same sums, two outputs per register pair
         if (warp_live) {
@@ -552,7 +582,7 @@ __global__ void __launch_bounds__(NT, (MODE == N_SWEEP) ? B200D_SEP_MIN_BLOCKS_S
                         for (int e = 0; e < 2; ++e) {
                             const int p = 2 * j + e;
                             const bool valid = (vb[q] >> (8 * p + s)) & 1u;
-                            if ((dcs[e] == 1) & valid) total[q][p] = add(total[q][p], 1.0f);   // :303-304
+                            tcnt += ((dcs[e] == 1) & valid ? 1u : 0u) << (4 * (q * PX + p));    // :303-304
                             und |= ((dcs[e] == 2) & valid ? 1u : 0u) << (q * PX + p);
                         }
                     }
@@ -587,7 +617,7 @@ __global__ void __launch_bounds__(NT, (MODE == N_SWEEP) ? B200D_SEP_MIN_BLOCKS_S
                 }
         }
         __syncthreads();                                   // h and stage st are free again
-        if (tid == 0 && s + 2 < S) {
+        if (!ONE && tid == 0 && s + 2 < S) {
             mbar_expect_tx(&bar[st], G::tile_bytes);
             tma_load_2d(s_r + (1 + st) * BUF, &a.tm_s[s + 2], &bar[st], cx, cy);
         }
@@ -616,7 +646,8 @@ __global__ void __launch_bounds__(NT, (MODE == N_SWEEP) ? B200D_SEP_MIN_BLOCKS_S
 #pragma unroll
         for (int q = 0; q < QY; ++q)
 #pragma unroll
-            for (int p = 0; p < PX; ++p) total[q][p] = add(total[q][p], (float)((extra >> (4 * (q * PX + p))) & 15u));
+            for (int p = 0; p < PX; ++p)                   // a (neighbour, output) pair counted either above or in the redo: <= 8 in total
+                total[q][p] = (float)(((tcnt + extra) >> (4 * (q * PX + p))) & 15u);
     }
 
     // ---- epilogue (same rules as ncc_kernel)
