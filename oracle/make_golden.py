@@ -224,5 +224,12 @@ if __name__ == '__main__':
                       n_src=5, seed=9, store_rng=True, store_costs=True)
     golden_patchmatch('patchmatch_tt_160x120_k11.npz', 'turntable', 9, 160, 120, k=11, iters=3, samples=8, ref_idx=4,
                       n_src=5, seed=123, store_rng=False, store_costs=False, arc=7.0)
+    # the remaining supported window sizes (9, 13): pins the oracle's window sums / NCC against the reference there too
+    golden_plane_sweep('planesweep_plane_60x44_k9.npz', 'plane', 5, 60, 44, D=8, k=9, ref_idx=2, dump_ncc=True)
+    golden_plane_sweep('planesweep_wavy_72x54_k13.npz', 'wavy', 5, 72, 54, D=8, k=13, ref_idx=1, dump_ncc=True)
+    golden_patchmatch('patchmatch_wavy_60x45_k9.npz', 'wavy', 5, 60, 45, k=9, iters=2, samples=3, ref_idx=2,
+                      n_src=4, seed=21, store_rng=True, store_costs=True)
+    golden_patchmatch('patchmatch_plane_64x48_k13.npz', 'plane', 6, 64, 48, k=13, iters=2, samples=2, ref_idx=3,
+                      n_src=5, seed=22, store_rng=True, store_costs=True)
     golden_host('host_heuristics.npz')
     golden_reconstruct('reconstruct_wavy_96x72.npz')

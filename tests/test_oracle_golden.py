@@ -14,11 +14,13 @@ from oracle import oracle as orc
 
 NCC_TOL = 5e-7          # observed max 2.4e-7; required by north_star: 1e-4
 
-SWEEPS = ['planesweep_plane_64x48_k5.npz', 'planesweep_wavy_80x60_k7.npz', 'planesweep_tt_161x97_k7.npz']
-PMS = ['patchmatch_wavy_64x48_k11.npz', 'patchmatch_plane_57x43_k5.npz', 'patchmatch_tt_160x120_k11.npz']
+SWEEPS = ['planesweep_plane_64x48_k5.npz', 'planesweep_wavy_80x60_k7.npz', 'planesweep_tt_161x97_k7.npz',
+          'planesweep_plane_60x44_k9.npz', 'planesweep_wavy_72x54_k13.npz']
+PMS = ['patchmatch_wavy_64x48_k11.npz', 'patchmatch_plane_57x43_k5.npz', 'patchmatch_tt_160x120_k11.npz',
+       'patchmatch_wavy_60x45_k9.npz', 'patchmatch_plane_64x48_k13.npz']
 
 
-@pytest.mark.parametrize('k', [3, 5, 7, 11])
+@pytest.mark.parametrize('k', [3, 5, 7, 9, 11, 13])
 def test_box_mean_matches_conv2d_bitexact(k):
     """F.conv2d(x, ones/k^2, padding=k//2) == row-major FMA chain (dense_stereo.py:325-341)."""
     import torch
