@@ -34,7 +34,8 @@ def _worker(rank, ws, port, q):
     try:
         mine = bdist.shard_views(VIEWS)
         my_pos = list(bdist.shard_positions(len(VIEWS)))
-        assert mine == [VIEWS[p] for p in my_pos] and my_pos == ([0, 1, 2, 3] if rank == 0 else [4, 5, 6])   # blocks
+        blocks = {2: [[0, 1, 2, 3], [4, 5, 6]], 3: [[0, 1, 2], [3, 4], [5, 6]]}[ws]                          # contiguous
+        assert mine == [VIEWS[p] for p in my_pos] and my_pos == blocks[rank]
         local = {v: _fake_cloud(v, COUNTS[v]) for v in mine if v != 8}     # view 8 missing entirely
         pts, col = bdist.gather_point_clouds(VIEWS, local, torch.device('cpu'))
         maps = bdist.all_gather_maps(VIEWS, {v: torch.full((3, 4), float(v)) for v in mine}, (3, 4), torch.device('cpu'))
@@ -63,9 +64,10 @@ def _worker(rank, ws, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.timeout(120)
-def test_gather_point_clouds_and_maps_world2():
-    ws, port = 2, _free_port()
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize('ws', [2, 3])
+def test_gather_point_clouds_and_maps_multi_rank(ws):
+    port = _free_port()
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, ws, port, q)) for r in range(ws)]
@@ -81,8 +83,9 @@ def test_gather_point_clouds_and_maps_world2():
     exp_p = np.concatenate([_fake_cloud(v, COUNTS[v])[0].numpy() for v in VIEWS])
     exp_c = np.concatenate([_fake_cloud(v, COUNTS[v])[1].numpy() for v in VIEWS])
     assert np.array_equal(res[0][0], exp_p) and np.array_equal(res[0][1], exp_c)     # sorted-view order on rank 0
-    assert res[1][0].shape == (0, 3) and res[1][1].shape == (0, 3)
-    assert res[0][2] and res[1][2]
+    for r in range(1, ws):
+        assert res[r][0].shape == (0, 3) and res[r][1].shape == (0, 3)
+    assert all(res[r][2] for r in range(ws))
 
 
 def test_single_process_paths():
