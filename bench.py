@@ -103,8 +103,10 @@ def config_dict(a, world):
                    'the bit-exact parity tests inject the reference\'s own draws, incl. at this 1600x1200 shape)',
             'l2': 'flushed between timed steps (512 MiB write)', 'views_in_flight': ns,
             'consistency': a.consistency,
-            'parallelism': f'view-sharded dp{world}' + (', fused clouds gathered to rank 0 every step (NCCL p2p '
-                                                        'into the final buffer)' if world > 1 else '')}
+            'parallelism': f'view-sharded dp{world}' + (' (contiguous blocks of views), fused clouds gathered to rank 0 '
+                                                        'every step (peer stores over NVLink into the final buffer; '
+                                                        'NCCL p2p where peer memory is unavailable: see gather_check)'
+                                                        if world > 1 else '')}
 
 
 def scene_for(a, ref_views, device, extra_views=()):
